@@ -1,0 +1,686 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (bf16 operands, fp32 accumulation in TMEM).
+//
+// Forward and data-gradient (one kernel; dgrad uses the mode-1 packed weight):
+//   GEMM view  M = N*H*W output pixels (CTA tile = 8x16 pixel rectangle = 128 rows),
+//              N = Cout (BN in {64,128,192,256}),  K = taps * (C0+C1), walked in blocks of 64 channels of one tap.
+//   A tile: one 4-D TMA box {64 ch, 16 x, 8 y, 1 n} of the NHWC activation, shifted by the tap offset; rows that
+//           fall outside the image are zero-filled by TMA, which is exactly the conv padding.  The box lands in
+//           shared memory as 128 rows x 128 B with the 128-byte swizzle = the UMMA K-major SW128 canonical layout.
+//   B tile: 2-D TMA box {64 k, BN rows} of the packed weight [Cout][taps*(C0+C1)].
+//   Warp roles: warp0 TMA producer, warp1 MMA issuer (one elected thread), warp2 TMEM allocator,
+//               warps4-7 epilogue (tcgen05.ld -> +bias (+residual) (ReLU) -> bf16 -> global NHWC).
+//   Persistent CTAs (grid = min(tiles, #SM)), STAGES-deep smem ring, two TMEM accumulators so that the epilogue
+//   of tile i overlaps the MMAs of tile i+1.
+//
+// Weight gradient:
+//   GEMM view  M = Cout (128 rows), N = Cin tile (BN), K = pixels, walked in blocks of 64 pixels (4x16 rectangle).
+//   Both operands are "MN-major" (the contiguous NHWC channel dim is M resp. N): dy tile and shifted-x tile are
+//   loaded as [64 px][64 ch] SW128 boxes and described with MN-major UMMA descriptors.  Split-K over CTAs, partial
+//   sums are added to the fp32 packed gradient with red.global.add.
+//
+// Replaces cuDNN behind F.conv2d / convolution_backward (networks.py:87, prob_unet.py:33).
+#include <cuda.h>
+
+#include <mutex>
+
+#include "../../include/probunet_b200.h"
+#include "common.cuh"
+#include "conv_internal.h"
+#include "tc_ptx.cuh"
+
+namespace pu {
+
+using namespace ptx;
+
+// ------------------------------------------------------------------------------------------------
+// tensor-map encoding through the driver entry point (no link-time dependency on libcuda)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    });
+    return fn;
+}
+
+// NHWC bf16 activation [N][H][W][C] -> 4-D map, box {64, bw, bh, 1}, 128B swizzle, zero OOB fill
+int make_act_tmap(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int bw, int bh) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled entry point not available");
+        return PU_ERR_CUDA;
+    }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(activation N=%d H=%d W=%d C=%d) failed: %d", N, H, W, C, (int)r);
+        return PU_ERR_CUDA;
+    }
+    return PU_OK;
+}
+
+// row-major bf16 matrix [rows][cols] -> 2-D map, box {64, brows}
+int make_mat_tmap(CUtensorMap* m, const void* ptr, long long rows, long long cols, int brows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled entry point not available");
+        return PU_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)brows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(matrix %lld x %lld) failed: %d", rows, cols, (int)r);
+        return PU_ERR_CUDA;
+    }
+    return PU_OK;
+}
+
+static int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward / dgrad kernel
+// ------------------------------------------------------------------------------------------------
+struct ConvTcParams {
+    int N, H, W, Cout, ksize;
+    int cblk0, cblks;       // 64-channel blocks in src0 / in src0||src1
+    int nkb;                // taps * cblks
+    int tiles_x, tiles_y, n_tiles, total_tiles;
+    int relu, bias_per_sample;
+    const float* bias;
+    const __nv_bfloat16* residual;
+    __nv_bfloat16* out;
+    double* gn_stats;
+    int gn_groups;
+};
+
+constexpr int TILE_W = 16, TILE_H = 8;      // 128 output pixels per CTA tile
+constexpr int A_BYTES = 128 * 128;          // 128 rows x 64 bf16
+
+template <int BN>
+struct ConvTcCfg {
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192) ? 5 : (BN == 128) ? 6 : 8;
+    static constexpr int ACC_STRIDE = (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
+    static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+    static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmB, const ConvTcParams p) {
+    using Cfg = ConvTcCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* tfull = bars + 2 * STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA0);
+        prefetch_tmap(&tmA1);
+        prefetch_tmap(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(smem_u32(&full[s]), 1);
+            mbar_init(smem_u32(&empty[s]), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&tfull[s]), 1);
+            mbar_init(smem_u32(&tempty[s]), 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(smem_u32(tmem_slot), Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int n_tile = tile % p.n_tiles;
+                int t = tile / p.n_tiles;
+                const int tx = t % p.tiles_x;
+                t /= p.tiles_x;
+                const int ty = t % p.tiles_y;
+                const int img = t / p.tiles_y;
+                const int x0 = tx * TILE_W, y0 = ty * TILE_H, n0 = n_tile * BN;
+                for (int kb = 0; kb < p.nkb; ++kb) {
+                    const int tap = kb / p.cblks;
+                    const int cb = kb - tap * p.cblks;
+                    const int dy = (p.ksize == 3) ? tap / 3 - 1 : 0;
+                    const int dx = (p.ksize == 3) ? tap % 3 - 1 : 0;
+                    mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+                    const uint32_t fb = smem_u32(&full[stage]);
+                    mbar_expect_tx(fb, A_BYTES + Cfg::B_BYTES);
+                    if (cb < p.cblk0)
+                        tma_load_4d(smem_u32(sA + stage * A_BYTES), &tmA0, fb, cb * 64, x0 + dx, y0 + dy, img);
+                    else
+                        tma_load_4d(smem_u32(sA + stage * A_BYTES), &tmA1, fb, (cb - p.cblk0) * 64, x0 + dx, y0 + dy,
+                                    img);
+                    tma_load_2d(smem_u32(sB + stage * Cfg::B_BYTES), &tmB, fb, kb * 64, n0);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t IDESC = idesc_bf16_f32(128, BN, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                mbar_wait(smem_u32(&tempty[acc]), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
+                for (int kb = 0; kb < p.nkb; ++kb) {
+                    mbar_wait(smem_u32(&full[stage]), phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(sA + stage * A_BYTES);
+                    const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t ad = smem_desc_sw128(a_addr + k * 32, 16, 1024);
+                        const uint64_t bd = smem_desc_sw128(b_addr + k * 32, 16, 1024);
+                        mma_f16_ss(d_tmem, ad, bd, IDESC, (kb | k) ? 1u : 0u);
+                    }
+                    mma_commit(smem_u32(&empty[stage]));
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                mma_commit(smem_u32(&tfull[acc]));
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp - 4;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const int n_tile = tile % p.n_tiles;
+            int t = tile / p.n_tiles;
+            const int tx = t % p.tiles_x;
+            t /= p.tiles_x;
+            const int ty = t % p.tiles_y;
+            const int img = t / p.tiles_y;
+            const int n0 = n_tile * BN;
+            const int r = q * 32 + lane;
+            const int py = ty * TILE_H + r / TILE_W;
+            const int px = tx * TILE_W + r % TILE_W;
+            const bool valid = (py < p.H) && (px < p.W);
+            const long long pix = ((long long)img * p.H + py) * p.W + px;
+            const float* bias = p.bias ? (p.bias + (p.bias_per_sample ? (long long)img * p.Cout : 0) + n0) : nullptr;
+
+            mbar_wait(smem_u32(&tfull[acc]), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_STRIDE;
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c, v);
+                tc_wait_ld();
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                if (bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] += __ldg(bias + c + j);
+                }
+                if (valid) {
+                    if (p.residual) {
+                        const __nv_bfloat16* rp = p.residual + pix * p.Cout + n0 + c;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            float rv[8];
+                            ld8(rp + j, rv);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) f[j + e] += rv[e];
+                        }
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                    }
+                    __nv_bfloat16* op = p.out + pix * p.Cout + n0 + c;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        float ov[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) ov[e] = f[j + e];
+                        st8(op + j, ov);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tempty[acc]));
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight-gradient kernel
+// ------------------------------------------------------------------------------------------------
+struct WgradTcParams {
+    int N, H, W, C0, C1, Cout, ksize;
+    int px_tiles_x, px_tiles_y;    // 4x16 pixel blocks per image
+    long long px_blocks;           // N * px_tiles_y * px_tiles_x
+    int co_tiles, ci_tiles, taps, splits;
+    long long blocks_per_split;
+    int total_items;
+    float* dw;
+};
+
+constexpr int WG_TW = 16, WG_TH = 4;        // 64 pixels per K block
+constexpr int WG_SUB = 64 * 128;            // one [64 px][64 ch] sub-tile = 8 KB
+
+template <int BN>
+struct WgradTcCfg {
+    static constexpr int A_BYTES_ = 2 * WG_SUB;
+    static constexpr int B_BYTES_ = (BN / 64) * WG_SUB;
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
+    static constexpr int ACC_STRIDE = (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
+    static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+    static constexpr int SMEM = STAGES * (A_BYTES_ + B_BYTES_) + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX0,
+                const __grid_constant__ CUtensorMap tmX1, const WgradTcParams p) {
+    using Cfg = WgradTcCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr int STAGE_BYTES = Cfg::A_BYTES_ + Cfg::B_BYTES_;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* tfull = bars + 2 * STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmDY);
+        prefetch_tmap(&tmX0);
+        prefetch_tmap(&tmX1);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(smem_u32(&full[s]), 1);
+            mbar_init(smem_u32(&empty[s]), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&tfull[s]), 1);
+            mbar_init(smem_u32(&tempty[s]), 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(smem_u32(tmem_slot), Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    const int Ctot = p.C0 + p.C1;
+
+    // item -> (split, tap, co_tile, ci_tile); splits outermost so that concurrently running CTAs share pixels
+    auto decode = [&](int item, int& split, int& tap, int& co_t, int& ci_t) {
+        ci_t = item % p.ci_tiles;
+        item /= p.ci_tiles;
+        co_t = item % p.co_tiles;
+        item /= p.co_tiles;
+        tap = item % p.taps;
+        split = item / p.taps;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+                int split, tap, co_t, ci_t;
+                decode(item, split, tap, co_t, ci_t);
+                const int dy = (p.ksize == 3) ? tap / 3 - 1 : 0;
+                const int dx = (p.ksize == 3) ? tap % 3 - 1 : 0;
+                long long b0 = (long long)split * p.blocks_per_split;
+                long long b1 = b0 + p.blocks_per_split;
+                if (b1 > p.px_blocks) b1 = p.px_blocks;
+                for (long long b = b0; b < b1; ++b) {
+                    const int bx = (int)(b % p.px_tiles_x);
+                    long long t = b / p.px_tiles_x;
+                    const int by = (int)(t % p.px_tiles_y);
+                    const int img = (int)(t / p.px_tiles_y);
+                    const int x0 = bx * WG_TW, y0 = by * WG_TH;
+                    mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+                    const uint32_t fb = smem_u32(&full[stage]);
+                    mbar_expect_tx(fb, STAGE_BYTES);
+                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    uint8_t* sb = sa + Cfg::A_BYTES_;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+                        tma_load_4d(smem_u32(sa + j * WG_SUB), &tmDY, fb, co_t * 128 + j * 64, x0, y0, img);
+#pragma unroll
+                    for (int j = 0; j < BN / 64; ++j) {
+                        const int c = ci_t * BN + j * 64;
+                        if (c < p.C0)
+                            tma_load_4d(smem_u32(sb + j * WG_SUB), &tmX0, fb, c, x0 + dx, y0 + dy, img);
+                        else
+                            tma_load_4d(smem_u32(sb + j * WG_SUB), &tmX1, fb, c - p.C0, x0 + dx, y0 + dy, img);
+                    }
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t IDESC = idesc_bf16_f32(128, BN, 1, 1);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+                int split, tap, co_t, ci_t;
+                decode(item, split, tap, co_t, ci_t);
+                long long b0 = (long long)split * p.blocks_per_split;
+                long long b1 = b0 + p.blocks_per_split;
+                if (b1 > p.px_blocks) b1 = p.px_blocks;
+                mbar_wait(smem_u32(&tempty[acc]), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
+                uint32_t first = 1;
+                for (long long b = b0; b < b1; ++b) {
+                    mbar_wait(smem_u32(&full[stage]), phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + Cfg::A_BYTES_;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        // MN-major SW128: 16 pixels (K) = 16 rows of 128 B; LBO = next 64-channel atom, SBO = 8 rows
+                        const uint64_t ad = smem_desc_sw128(a_addr + k * 2048, WG_SUB, 1024);
+                        const uint64_t bd = smem_desc_sw128(b_addr + k * 2048, WG_SUB, 1024);
+                        mma_f16_ss(d_tmem, ad, bd, IDESC, (first && k == 0) ? 0u : 1u);
+                    }
+                    first = 0;
+                    mma_commit(smem_u32(&empty[stage]));
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                mma_commit(smem_u32(&tfull[acc]));
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp - 4;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const long long row_stride = (long long)p.taps * Ctot;
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+            int split, tap, co_t, ci_t;
+            decode(item, split, tap, co_t, ci_t);
+            long long b0 = (long long)split * p.blocks_per_split;
+            const bool has_work = b0 < p.px_blocks;
+            const int co = co_t * 128 + q * 32 + lane;
+            mbar_wait(smem_u32(&tfull[acc]), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_STRIDE;
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c, v);
+                tc_wait_ld();
+                if (has_work && co < p.Cout) {
+                    float* dst = p.dw + co * row_stride + (long long)tap * Ctot + ci_t * BN + c;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (ci_t * BN + c + j < Ctot) atomicAdd(dst + j, __uint_as_float(v[j]));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tempty[acc]));
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static bool tc_device_ok() {
+    static int ok = -1;
+    if (ok < 0) ok = pu_device_supports_tc();
+    return ok == 1;
+}
+
+bool conv_tc_applicable(const PuConvArgs* a) {
+    if (a->dtype != PU_BF16 || !tc_device_ok()) return false;
+    if (a->ksize != 1 && a->ksize != 3) return false;
+    if (a->C0 <= 0 || a->C0 % 64 || a->C1 % 64 || a->Cout % 64) return false;
+    if (a->W < TILE_W || a->H < TILE_H) return false;   // tiny test images: CUDA-core kernel
+    if (a->gn_stats) return false;
+    return true;
+}
+
+template <int BN>
+static int conv_tc_launch_bn(const PuConvArgs* a, cudaStream_t st) {
+    using Cfg = ConvTcCfg<BN>;
+    ConvTcParams p;
+    p.N = a->N; p.H = a->H; p.W = a->W; p.Cout = a->Cout; p.ksize = a->ksize;
+    p.cblk0 = a->C0 / 64;
+    p.cblks = (a->C0 + a->C1) / 64;
+    p.nkb = a->ksize * a->ksize * p.cblks;
+    p.tiles_x = cdiv(a->W, TILE_W);
+    p.tiles_y = cdiv(a->H, TILE_H);
+    p.n_tiles = a->Cout / BN;
+    long long total = (long long)a->N * p.tiles_x * p.tiles_y * p.n_tiles;
+    PU_REQUIRE(total < (1LL << 31), "conv_tc: too many tiles");
+    p.total_tiles = (int)total;
+    p.relu = (a->flags & PU_CONV_RELU) ? 1 : 0;
+    p.bias_per_sample = a->bias_per_sample;
+    p.bias = a->bias;
+    p.residual = (const __nv_bfloat16*)a->residual;
+    p.out = (__nv_bfloat16*)a->out;
+    p.gn_stats = a->gn_stats;
+    p.gn_groups = a->gn_groups;
+
+    CUtensorMap tA0, tA1, tB;
+    int rc = make_act_tmap(&tA0, a->src0, a->N, a->H, a->W, a->C0, TILE_W, TILE_H);
+    if (rc) return rc;
+    if (a->C1 > 0)
+        rc = make_act_tmap(&tA1, a->src1, a->N, a->H, a->W, a->C1, TILE_W, TILE_H);
+    else
+        tA1 = tA0;
+    if (rc) return rc;
+    rc = make_mat_tmap(&tB, a->weight, a->Cout, (long long)a->ksize * a->ksize * (a->C0 + a->C1), BN);
+    if (rc) return rc;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        PU_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        attr_set = true;
+    }
+    int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+    conv_tc_kernel<BN><<<grid, 256, Cfg::SMEM, st>>>(tA0, tA1, tB, p);
+    return check_launch("conv_tc");
+}
+
+int conv_tc_launch(const PuConvArgs* a, cudaStream_t st) {
+    if (a->Cout % 256 == 0) return conv_tc_launch_bn<256>(a, st);
+    if (a->Cout % 192 == 0) return conv_tc_launch_bn<192>(a, st);
+    if (a->Cout % 128 == 0) return conv_tc_launch_bn<128>(a, st);
+    return conv_tc_launch_bn<64>(a, st);
+}
+
+bool wgrad_tc_applicable(const PuWgradArgs* a) {
+    if (a->dtype != PU_BF16 || !tc_device_ok()) return false;
+    if (a->ksize != 1 && a->ksize != 3) return false;
+    if (a->C0 <= 0 || a->C0 % 64 || a->C1 % 64 || a->Cout % 64) return false;
+    if (a->W < WG_TW || a->H < WG_TH) return false;
+    return true;
+}
+
+template <int BN>
+static int wgrad_tc_launch_bn(const PuWgradArgs* a, cudaStream_t st) {
+    using Cfg = WgradTcCfg<BN>;
+    WgradTcParams p;
+    p.N = a->N; p.H = a->H; p.W = a->W; p.C0 = a->C0; p.C1 = a->C1; p.Cout = a->Cout; p.ksize = a->ksize;
+    p.px_tiles_x = cdiv(a->W, WG_TW);
+    p.px_tiles_y = cdiv(a->H, WG_TH);
+    p.px_blocks = (long long)a->N * p.px_tiles_x * p.px_tiles_y;
+    p.co_tiles = cdiv(a->Cout, 128);
+    p.ci_tiles = cdiv(a->C0 + a->C1, BN);
+    p.taps = a->ksize * a->ksize;
+    int base_items = p.co_tiles * p.ci_tiles * p.taps;
+    long long want = cdivll(2LL * num_sms(), base_items);
+    long long max_split = cdivll(p.px_blocks, 8);   // at least 8 K-blocks (512 pixels) per item
+    if (max_split < 1) max_split = 1;
+    long long splits = want < 1 ? 1 : (want > max_split ? max_split : want);
+    p.blocks_per_split = cdivll(p.px_blocks, splits);
+    p.splits = (int)cdivll(p.px_blocks, p.blocks_per_split);
+    p.total_items = base_items * p.splits;
+    p.dw = a->dw;
+
+    CUtensorMap tDY, tX0, tX1;
+    int rc = make_act_tmap(&tDY, a->dy, a->N, a->H, a->W, a->Cout, WG_TW, WG_TH);
+    if (rc) return rc;
+    rc = make_act_tmap(&tX0, a->src0, a->N, a->H, a->W, a->C0, WG_TW, WG_TH);
+    if (rc) return rc;
+    if (a->C1 > 0)
+        rc = make_act_tmap(&tX1, a->src1, a->N, a->H, a->W, a->C1, WG_TW, WG_TH);
+    else
+        tX1 = tX0;
+    if (rc) return rc;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        PU_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        attr_set = true;
+    }
+    int grid = p.total_items < num_sms() ? p.total_items : num_sms();
+    wgrad_tc_kernel<BN><<<grid, 256, Cfg::SMEM, st>>>(tDY, tX0, tX1, p);
+    return check_launch("wgrad_tc");
+}
+
+int wgrad_tc_launch(const PuWgradArgs* a, cudaStream_t st) {
+    int Ctot = a->C0 + a->C1;
+    if (Ctot % 256 == 0) return wgrad_tc_launch_bn<256>(a, st);
+    if (Ctot % 128 == 0) return wgrad_tc_launch_bn<128>(a, st);
+    return wgrad_tc_launch_bn<64>(a, st);
+}
+
+}  // namespace pu
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" int pu_conv2d(const PuConvArgs* a, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PU_REQUIRE(a && a->src0 && a->weight && a->out, "pu_conv2d: null pointer");
+    PU_REQUIRE(a->N > 0 && a->H > 0 && a->W > 0 && a->C0 > 0 && a->C1 >= 0 && a->Cout > 0, "pu_conv2d: bad shape");
+    PU_REQUIRE(a->ksize == 1 || a->ksize == 3, "pu_conv2d: ksize must be 1 or 3 (got %d)", a->ksize);
+    PU_REQUIRE(a->dtype == PU_F32 || a->dtype == PU_BF16, "pu_conv2d: bad dtype %d", a->dtype);
+    PU_REQUIRE(a->C1 == 0 || a->src1, "pu_conv2d: C1 > 0 needs src1");
+    bool tc = pu::conv_tc_applicable(a) && !(a->flags & PU_CONV_FORCE_SIMPLE);
+    if (a->flags & PU_CONV_FORCE_TC)
+        PU_REQUIRE(tc, "pu_conv2d: PU_CONV_FORCE_TC but the tcgen05 kernel does not apply (dtype=%d C0=%d C1=%d Cout=%d)",
+                   a->dtype, a->C0, a->C1, a->Cout);
+    if (tc) return pu::conv_tc_launch(a, st);
+    PU_REQUIRE(!a->gn_stats, "pu_conv2d: gn_stats fusion needs the tcgen05 kernel");
+    return pu::conv_simple_launch(a, st);
+}
+
+extern "C" int pu_conv2d_wgrad(const PuWgradArgs* a, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PU_REQUIRE(a && a->src0 && a->dy && a->dw, "pu_conv2d_wgrad: null pointer");
+    PU_REQUIRE(a->N > 0 && a->H > 0 && a->W > 0 && a->C0 > 0 && a->C1 >= 0 && a->Cout > 0, "pu_conv2d_wgrad: bad shape");
+    PU_REQUIRE(a->ksize == 1 || a->ksize == 3, "pu_conv2d_wgrad: ksize must be 1 or 3");
+    PU_REQUIRE(a->C1 == 0 || a->src1, "pu_conv2d_wgrad: C1 > 0 needs src1");
+    size_t n = (size_t)a->Cout * a->ksize * a->ksize * (a->C0 + a->C1);
+    if (!a->accumulate) PU_CUDA(cudaMemsetAsync(a->dw, 0, n * sizeof(float), st));
+    bool tc = pu::wgrad_tc_applicable(a) && !(a->flags & PU_CONV_FORCE_SIMPLE);
+    if (a->flags & PU_CONV_FORCE_TC) PU_REQUIRE(tc, "pu_conv2d_wgrad: PU_CONV_FORCE_TC but tcgen05 kernel does not apply");
+    if (tc) return pu::wgrad_tc_launch(a, st);
+    return pu::wgrad_simple_launch(a, st);
+}

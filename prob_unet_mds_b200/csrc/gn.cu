@@ -1,0 +1,460 @@
+// GroupNorm (+adaptive scale/shift, SiLU, dropout, 2x resample) forward and backward, NHWC, HBM-bound.
+// Replaces F.group_norm / silu / addcmul / dropout and the depthwise resample convs around them
+// (networks.py:104,166,170-171,175,82-85).  Statistics are accumulated in fp64.
+#include "../../include/probunet_b200.h"
+#include "common.cuh"
+
+namespace pu {
+
+constexpr int GN_THREADS = 256;
+
+// ---- helpers shared by forward and backward ----
+struct GnSmem {
+    float* mu;    // [C] group mean per channel
+    float* rstd;  // [C]
+    float* gam;   // [C] gamma' = gamma * (1 + scale)
+    float* bet;   // [C] beta'  = beta * (1 + scale) + shift
+};
+
+__device__ __forceinline__ GnSmem gn_smem(float* base, int C) {
+    GnSmem s;
+    s.mu = base;
+    s.rstd = base + C;
+    s.gam = base + 2 * C;
+    s.bet = base + 3 * C;
+    return s;
+}
+
+__device__ __forceinline__ void gn_setup(const PuGnArgs& f, int n, const GnSmem& s) {
+    const int C = f.C0 + f.C1;
+    const int Cg = C / f.G;
+    const double m = (double)Cg * f.H * f.W;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / Cg;
+        const double sum = f.stats[((long long)n * f.G + g) * 2];
+        const double ssq = f.stats[((long long)n * f.G + g) * 2 + 1];
+        const double mean = sum / m;
+        double var = ssq / m - mean * mean;
+        if (var < 0) var = 0;
+        float gam = f.gamma[c], bet = f.beta[c];
+        if (f.ada) {
+            const float sc = f.ada[c], sh = f.ada[C + c];
+            gam = gam * (1.f + sc);
+            bet = fmaf(bet, 1.f + sc, sh);
+        }
+        s.mu[c] = (float)mean;
+        s.rstd[c] = (float)(1.0 / sqrt(var + (double)f.eps));
+        s.gam[c] = gam;
+        s.bet[c] = bet;
+    }
+    __syncthreads();
+}
+
+template <typename T>
+__device__ __forceinline__ void gn_load_x8(const PuGnArgs& f, long long pix, int c0, float (&v)[8]) {
+    if (c0 < f.C0)
+        ld8(reinterpret_cast<const T*>(f.src0) + pix * f.C0 + c0, v);
+    else
+        ld8(reinterpret_cast<const T*>(f.src1) + pix * f.C1 + (c0 - f.C0), v);
+}
+
+// ---- statistics ----
+template <typename T>
+__global__ void __launch_bounds__(GN_THREADS)
+gn_stats_kernel(const T* __restrict__ s0, const T* __restrict__ s1, int C0, int C1, int HW, int G, int rows,
+                double* __restrict__ stats) {
+    extern __shared__ float sm[];   // [G][2]
+    const int C = C0 + C1, nvec = C / 8, Cg = C / G;
+    const int n = blockIdx.y;
+    const int PL = GN_THREADS / nvec;
+    const int v = threadIdx.x % nvec, pl = threadIdx.x / nvec;
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    const int r0 = blockIdx.x * rows;
+    int r1 = r0 + rows;
+    if (r1 > HW) r1 = HW;
+    if (pl < PL) {
+        float s[8], q[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+        const int c0 = v * 8;
+        for (int r = r0 + pl; r < r1; r += PL) {
+            const long long pix = (long long)n * HW + r;
+            float x[8];
+            if (c0 < C0)
+                ld8(s0 + pix * C0 + c0, x);
+            else
+                ld8(s1 + pix * C1 + (c0 - C0), x);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                s[e] += x[e];
+                q[e] = fmaf(x[e], x[e], q[e]);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int g = (c0 + e) / Cg;
+            atomicAdd(&sm[2 * g], s[e]);
+            atomicAdd(&sm[2 * g + 1], q[e]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(stats + (long long)n * G * 2 + i, (double)sm[i]);
+}
+
+// ---- forward apply ----
+template <typename T>
+__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(PuGnArgs f, int rows) {
+    extern __shared__ float sm[];
+    const int C = f.C0 + f.C1, nvec = C / 8;
+    const int n = blockIdx.y;
+    GnSmem s = gn_smem(sm, C);
+    gn_setup(f, n, s);
+    const int OH = f.resample == PU_RS_UP ? f.H * 2 : (f.resample == PU_RS_DOWN ? f.H / 2 : f.H);
+    const int OW = f.resample == PU_RS_UP ? f.W * 2 : (f.resample == PU_RS_DOWN ? f.W / 2 : f.W);
+    const int r0 = blockIdx.x * rows;
+    int r1 = r0 + rows;
+    if (r1 > OH * OW) r1 = OH * OW;
+    const float inv_keep = f.dropout_p > 0.f ? 1.f / (1.f - f.dropout_p) : 1.f;
+    T* y = reinterpret_cast<T*>(f.y);
+    const int total = (r1 - r0) * nvec;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int v = idx % nvec;
+        const int op = r0 + idx / nvec;
+        const int oy = op / OW, ox = op % OW;
+        const int c0 = v * 8;
+        float o[8];
+        if (f.resample == PU_RS_DOWN) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = 0.f;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int iy = oy * 2 + (t >> 1), ix = ox * 2 + (t & 1);
+                float x[8];
+                gn_load_x8<T>(f, ((long long)n * f.H + iy) * f.W + ix, c0, x);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    float u = fmaf((x[e] - s.mu[c0 + e]) * s.rstd[c0 + e], s.gam[c0 + e], s.bet[c0 + e]);
+                    o[e] += f.silu ? silu_f(u) : u;
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] *= 0.25f;
+        } else {
+            const int iy = f.resample == PU_RS_UP ? (oy >> 1) : oy;
+            const int ix = f.resample == PU_RS_UP ? (ox >> 1) : ox;
+            float x[8];
+            gn_load_x8<T>(f, ((long long)n * f.H + iy) * f.W + ix, c0, x);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float u = fmaf((x[e] - s.mu[c0 + e]) * s.rstd[c0 + e], s.gam[c0 + e], s.bet[c0 + e]);
+                o[e] = f.silu ? silu_f(u) : u;
+            }
+        }
+        const long long opix = (long long)n * OH * OW + op;
+        if (f.dropout_p > 0.f) {
+            const uint32_t keep = dropout_keep8(f.seed, (unsigned long long)((opix * C + c0) >> 3), f.dropout_p);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = ((keep >> e) & 1u) ? o[e] * inv_keep : 0.f;
+        }
+        st8(y + opix * C + c0, o);
+    }
+}
+
+// ---- backward ----
+// gradient wrt the (pre-resample) activation output at input pixel (iy, ix): gathers dy through the transpose
+// of the forward resample
+template <typename T>
+__device__ __forceinline__ void gn_gather8(const T* dy, int rs, int n, int H, int W, int iy, int ix, int C, int c0,
+                                           float (&g)[8]) {
+    if (rs == PU_RS_NONE) {
+        ld8(dy + (((long long)n * H + iy) * W + ix) * C + c0, g);
+    } else if (rs == PU_RS_UP) {
+        const int OH = 2 * H, OW = 2 * W;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) g[e] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            float v[8];
+            ld8(dy + (((long long)n * OH + 2 * iy + (t >> 1)) * OW + 2 * ix + (t & 1)) * C + c0, v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) g[e] += v[e];
+        }
+    } else {
+        const int OH = H / 2, OW = W / 2;
+        ld8(dy + (((long long)n * OH + (iy >> 1)) * OW + (ix >> 1)) * C + c0, g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) g[e] *= 0.25f;
+    }
+}
+
+// du = d loss / d u  where u = xhat * gamma' + beta' and y = resample(dropout(act(u)))
+template <typename T>
+__device__ __forceinline__ void gn_du8(const PuGnArgs& f, const GnSmem& s, const T* dy, int n, int iy, int ix, int c0,
+                                       float (&xh)[8], float (&du)[8]) {
+    const int C = f.C0 + f.C1;
+    const long long pix = ((long long)n * f.H + iy) * f.W + ix;
+    float x[8], g[8];
+    gn_load_x8<T>(f, pix, c0, x);
+    gn_gather8<T>(dy, f.resample, n, f.H, f.W, iy, ix, C, c0, g);
+    uint32_t keep = 0xffu;
+    float inv_keep = 1.f;
+    if (f.dropout_p > 0.f) {
+        keep = dropout_keep8(f.seed, (unsigned long long)((pix * C + c0) >> 3), f.dropout_p);
+        inv_keep = 1.f / (1.f - f.dropout_p);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        xh[e] = (x[e] - s.mu[c0 + e]) * s.rstd[c0 + e];
+        float gg = ((keep >> e) & 1u) ? g[e] * inv_keep : 0.f;
+        if (f.silu) {
+            float u = fmaf(xh[e], s.gam[c0 + e], s.bet[c0 + e]);
+            gg *= dsilu_f(u);
+        }
+        du[e] = gg;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(GN_THREADS) gn_bwd_reduce_kernel(PuGnBwdArgs a, int rows) {
+    extern __shared__ float sm[];
+    const PuGnArgs& f = a.f;
+    const int C = f.C0 + f.C1, nvec = C / 8;
+    const int n = blockIdx.y;
+    GnSmem s = gn_smem(sm, C);
+    float* red = sm + 4 * C;   // [C][2]
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
+    gn_setup(f, n, s);
+    const int PL = GN_THREADS / nvec;
+    const int v = threadIdx.x % nvec, pl = threadIdx.x / nvec;
+    const int HW = f.H * f.W;
+    const int r0 = blockIdx.x * rows;
+    int r1 = r0 + rows;
+    if (r1 > HW) r1 = HW;
+    const T* dy = reinterpret_cast<const T*>(a.dy);
+    if (pl < PL) {
+        const int c0 = v * 8;
+        float A[8], B[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) A[e] = B[e] = 0.f;
+        for (int r = r0 + pl; r < r1; r += PL) {
+            float xh[8], du[8];
+            gn_du8<T>(f, s, dy, n, r / f.W, r % f.W, c0, xh, du);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                A[e] += du[e];
+                B[e] = fmaf(du[e], xh[e], B[e]);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            atomicAdd(&red[2 * (c0 + e)], A[e]);
+            atomicAdd(&red[2 * (c0 + e) + 1], B[e]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(a.sums + (long long)n * C * 2 + i, red[i]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(PuGnBwdArgs a, int rows) {
+    extern __shared__ float sm[];
+    const PuGnArgs& f = a.f;
+    const int C = f.C0 + f.C1, nvec = C / 8, Cg = C / f.G;
+    const int n = blockIdx.y;
+    GnSmem s = gn_smem(sm, C);
+    float* S = sm + 4 * C;   // [G][2]: sum_c gamma' A, sum_c gamma' B
+    for (int i = threadIdx.x; i < 2 * f.G; i += blockDim.x) S[i] = 0.f;
+    gn_setup(f, n, s);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / Cg;
+        atomicAdd(&S[2 * g], s.gam[c] * a.sums[((long long)n * C + c) * 2]);
+        atomicAdd(&S[2 * g + 1], s.gam[c] * a.sums[((long long)n * C + c) * 2 + 1]);
+    }
+    __syncthreads();
+    const float inv_m = 1.f / ((float)Cg * (float)f.H * (float)f.W);
+    const int HW = f.H * f.W;
+    const int r0 = blockIdx.x * rows;
+    int r1 = r0 + rows;
+    if (r1 > HW) r1 = HW;
+    const T* dy = reinterpret_cast<const T*>(a.dy);
+    const T* dres = reinterpret_cast<const T*>(a.dres);
+    T* dx0 = reinterpret_cast<T*>(a.dx0);
+    T* dx1 = reinterpret_cast<T*>(a.dx1);
+    const int total = (r1 - r0) * nvec;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int v = idx % nvec;
+        const int r = r0 + idx / nvec;
+        const int iy = r / f.W, ix = r % f.W;
+        const int c0 = v * 8;
+        float xh[8], du[8], o[8];
+        gn_du8<T>(f, s, dy, n, iy, ix, c0, xh, du);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int g = (c0 + e) / Cg;
+            const float dxh = du[e] * s.gam[c0 + e];
+            o[e] = s.rstd[c0 + e] * (dxh - S[2 * g] * inv_m - xh[e] * S[2 * g + 1] * inv_m);
+        }
+        if (dres) {
+            float d[8];
+            gn_gather8<T>(dres, a.dres_resample, n, f.H, f.W, iy, ix, C, c0, d);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] += d[e];
+        }
+        const long long pix = (long long)n * HW + r;
+        T* dst;
+        int acc;
+        if (c0 < f.C0) {
+            dst = dx0 + pix * f.C0 + c0;
+            acc = a.acc0;
+        } else {
+            dst = dx1 + pix * f.C1 + (c0 - f.C0);
+            acc = a.acc1;
+        }
+        if (acc) {
+            float old[8];
+            ld8(dst, old);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] += old[e];
+        }
+        st8(dst, o);
+    }
+}
+
+__global__ void gn_bwd_params_kernel(PuGnBwdArgs a) {
+    const PuGnArgs& f = a.f;
+    const int C = f.C0 + f.C1;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float sa = 0.f, sb = 0.f;
+    for (int n = 0; n < f.N; ++n) {
+        sa += a.sums[((long long)n * C + c) * 2];
+        sb += a.sums[((long long)n * C + c) * 2 + 1];
+    }
+    const float sc = f.ada ? f.ada[c] : 0.f;
+    const float dg = (1.f + sc) * sb, db = (1.f + sc) * sa;
+    if (a.acc_params) {
+        a.dgamma[c] += dg;
+        a.dbeta[c] += db;
+    } else {
+        a.dgamma[c] = dg;
+        a.dbeta[c] = db;
+    }
+    if (f.ada && a.dada) {
+        const float ds = f.gamma[c] * sb + f.beta[c] * sa;
+        if (a.acc_params) {
+            a.dada[c] += ds;
+            a.dada[C + c] += sa;
+        } else {
+            a.dada[c] = ds;
+            a.dada[C + c] = sa;
+        }
+    }
+}
+
+static int rows_per_block(int HW, int N, int min_rows) {
+    int target_blocks = (148 * 8) / (N > 0 ? N : 1);
+    if (target_blocks < 1) target_blocks = 1;
+    int rows = cdiv(HW, target_blocks);
+    if (rows < min_rows) rows = min_rows;
+    return rows;
+}
+
+static int check_gn(const PuGnArgs& f, const char* who) {
+    const int C = f.C0 + f.C1;
+    PU_REQUIRE(f.src0 && f.stats && f.gamma && f.beta, "%s: null pointer", who);
+    PU_REQUIRE(f.N > 0 && f.H > 0 && f.W > 0 && f.C0 > 0 && f.C1 >= 0 && f.G > 0, "%s: bad shape", who);
+    PU_REQUIRE(f.C0 % 8 == 0 && f.C1 % 8 == 0 && C % f.G == 0 && C / 8 <= GN_THREADS,
+               "%s: channels (%d,%d) must be multiples of 8, divisible by G=%d, and <= %d", who, f.C0, f.C1, f.G,
+               GN_THREADS * 8);
+    PU_REQUIRE(f.C1 == 0 || f.src1, "%s: C1 > 0 needs src1", who);
+    PU_REQUIRE(f.resample != PU_RS_DOWN || (f.H % 2 == 0 && f.W % 2 == 0), "%s: downsample needs even H, W", who);
+    PU_REQUIRE(f.dropout_p == 0.f || f.resample == PU_RS_NONE, "%s: dropout with resample is not supported", who);
+    PU_REQUIRE(f.dropout_p >= 0.f && f.dropout_p < 1.f, "%s: bad dropout p", who);
+    PU_REQUIRE(f.dtype == PU_F32 || f.dtype == PU_BF16, "%s: bad dtype", who);
+    return PU_OK;
+}
+
+}  // namespace pu
+
+extern "C" {
+
+int pu_gn_stats(const void* src0, const void* src1, int C0, int C1, int N, int HW, int G, int dtype, double* stats,
+                void* stream) {
+    using namespace pu;
+    const int C = C0 + C1;
+    PU_REQUIRE(src0 && stats && N > 0 && HW > 0 && C0 > 0 && C1 >= 0 && G > 0, "pu_gn_stats: bad arguments");
+    PU_REQUIRE(C0 % 8 == 0 && C1 % 8 == 0 && C % G == 0 && C / 8 <= GN_THREADS, "pu_gn_stats: unsupported channels");
+    PU_REQUIRE(C1 == 0 || src1, "pu_gn_stats: C1 > 0 needs src1");
+    cudaStream_t st = (cudaStream_t)stream;
+    PU_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * N * G, st));
+    const int PL = GN_THREADS / (C / 8);
+    const int rows = rows_per_block(HW, N, PL * 4);
+    dim3 grid(cdiv(HW, rows), N);
+    const size_t smem = sizeof(float) * 2 * G;
+    if (dtype == PU_F32)
+        gn_stats_kernel<float><<<grid, GN_THREADS, smem, st>>>((const float*)src0, (const float*)src1, C0, C1, HW, G, rows,
+                                                               stats);
+    else
+        gn_stats_kernel<__nv_bfloat16><<<grid, GN_THREADS, smem, st>>>((const __nv_bfloat16*)src0,
+                                                                       (const __nv_bfloat16*)src1, C0, C1, HW, G, rows,
+                                                                       stats);
+    return check_launch("gn_stats");
+}
+
+int pu_gn_apply(const PuGnArgs* a, void* stream) {
+    using namespace pu;
+    PU_REQUIRE(a && a->y, "pu_gn_apply: null pointer");
+    int rc = check_gn(*a, "pu_gn_apply");
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int C = a->C0 + a->C1;
+    const int OHW = a->resample == PU_RS_UP ? a->H * a->W * 4 : (a->resample == PU_RS_DOWN ? a->H * a->W / 4 : a->H * a->W);
+    const int rows = rows_per_block(OHW, a->N, 8);
+    dim3 grid(cdiv(OHW, rows), a->N);
+    const size_t smem = sizeof(float) * 4 * C;
+    if (a->dtype == PU_F32)
+        gn_apply_kernel<float><<<grid, GN_THREADS, smem, st>>>(*a, rows);
+    else
+        gn_apply_kernel<__nv_bfloat16><<<grid, GN_THREADS, smem, st>>>(*a, rows);
+    return check_launch("gn_apply");
+}
+
+int pu_gn_bwd(const PuGnBwdArgs* a, void* stream) {
+    using namespace pu;
+    PU_REQUIRE(a && a->dy && a->sums && a->dx0 && a->dgamma && a->dbeta, "pu_gn_bwd: null pointer");
+    int rc = check_gn(a->f, "pu_gn_bwd");
+    if (rc) return rc;
+    const PuGnArgs& f = a->f;
+    PU_REQUIRE(f.C1 == 0 || a->dx1, "pu_gn_bwd: C1 > 0 needs dx1");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int C = f.C0 + f.C1;
+    const int HW = f.H * f.W;
+    PU_CUDA(cudaMemsetAsync(a->sums, 0, sizeof(float) * 2 * f.N * C, st));
+    const int PL = GN_THREADS / (C / 8);
+    {
+        const int rows = rows_per_block(HW, f.N, PL * 4);
+        dim3 grid(cdiv(HW, rows), f.N);
+        const size_t smem = sizeof(float) * 6 * C;
+        if (f.dtype == PU_F32)
+            gn_bwd_reduce_kernel<float><<<grid, GN_THREADS, smem, st>>>(*a, rows);
+        else
+            gn_bwd_reduce_kernel<__nv_bfloat16><<<grid, GN_THREADS, smem, st>>>(*a, rows);
+        rc = check_launch("gn_bwd_reduce");
+        if (rc) return rc;
+    }
+    {
+        const int rows = rows_per_block(HW, f.N, 8);
+        dim3 grid(cdiv(HW, rows), f.N);
+        const size_t smem = sizeof(float) * (4 * C + 2 * f.G);
+        if (f.dtype == PU_F32)
+            gn_bwd_apply_kernel<float><<<grid, GN_THREADS, smem, st>>>(*a, rows);
+        else
+            gn_bwd_apply_kernel<__nv_bfloat16><<<grid, GN_THREADS, smem, st>>>(*a, rows);
+        rc = check_launch("gn_bwd_apply");
+        if (rc) return rc;
+    }
+    gn_bwd_params_kernel<<<cdiv(C, 128), 128, 0, st>>>(*a);
+    return check_launch("gn_bwd_params");
+}
+}

@@ -1,0 +1,163 @@
+// Layout conversion and weight packing kernels (pure data movement, HBM bound, tiny next to the convs).
+#include "../../include/probunet_b200.h"
+#include "common.cuh"
+
+namespace pu {
+
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int N, int C, int HW, int Cdst,
+                                    int c_off) {
+    long long total = (long long)N * HW * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        long long t = i / C;
+        int hw = (int)(t % HW);
+        int n = (int)(t / HW);
+        stf(dst + ((long long)n * HW + hw) * Cdst + c_off + c, src[((long long)n * C + c) * HW + hw]);
+    }
+}
+
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int N, int C, int HW) {
+    long long total = (long long)N * HW * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int hw = (int)(i % HW);
+        long long t = i / HW;
+        int c = (int)(t % C);
+        int n = (int)(t / C);
+        dst[i] = ldf(src + ((long long)n * HW + hw) * C + c);
+    }
+}
+
+template <typename T>
+__global__ void pack_weight_kernel(const float* __restrict__ src, T* __restrict__ dst, int Co, int Ci, int k, int Ci_pad,
+                                   int mode, const int* __restrict__ perm, long long src_co_stride) {
+    const int kk = k * k;
+    long long total = (mode == 0) ? (long long)Co * kk * Ci_pad : (long long)Ci * kk * Co;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        float v = 0.f;
+        if (mode == 0) {
+            int ci = (int)(i % Ci_pad);
+            long long t = i / Ci_pad;
+            int tap = (int)(t % kk);
+            int co = (int)(t / kk);
+            if (ci < Ci) {
+                int sco = perm ? perm[co] : co;
+                v = src[(long long)sco * src_co_stride + (long long)ci * kk + tap];
+            }
+        } else {
+            int co = (int)(i % Co);
+            long long t = i / Co;
+            int tap = (int)(t % kk);
+            int ci = (int)(t / kk);
+            int sco = perm ? perm[co] : co;
+            v = src[(long long)sco * src_co_stride + (long long)ci * kk + (kk - 1 - tap)];
+        }
+        stf(dst + i, v);
+    }
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ src, float* __restrict__ dst, int Co, int Ci, int k,
+                                    int Ci_pad, const int* __restrict__ perm, int accumulate, long long dst_co_stride) {
+    const int kk = k * k;
+    long long total = (long long)Co * Ci * kk;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int tap = (int)(i % kk);
+        long long t = i / kk;
+        int ci = (int)(t % Ci);
+        int co = (int)(t / Ci);
+        int dco = perm ? perm[co] : co;
+        float v = src[((long long)co * kk + tap) * Ci_pad + ci];
+        float* d = dst + (long long)dco * dst_co_stride + (long long)ci * kk + tap;
+        *d = accumulate ? (*d + v) : v;
+    }
+}
+
+__global__ void gather_kernel(const float* src, const int* perm, float* dst, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[perm[i]];
+}
+__global__ void scatter_kernel(const float* src, const int* perm, float* dst, int n, int accumulate) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        float* d = dst + perm[i];
+        *d = accumulate ? (*d + src[i]) : src[i];
+    }
+}
+
+static unsigned grid_for(long long total, int threads = 256) {
+    long long g = cdivll(total, threads);
+    if (g > 148LL * 16) g = 148LL * 16;
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+
+}  // namespace pu
+
+extern "C" {
+
+int pu_nchw_to_nhwc(const float* src, void* dst, int N, int C, int H, int W, int Cdst, int c_off, int dst_dtype,
+                    void* stream) {
+    PU_REQUIRE(src && dst && N > 0 && C > 0 && H > 0 && W > 0 && c_off >= 0 && c_off + C <= Cdst,
+               "pu_nchw_to_nhwc: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    long long total = (long long)N * C * H * W;
+    if (dst_dtype == PU_F32)
+        pu::nchw_to_nhwc_kernel<float><<<pu::grid_for(total), 256, 0, st>>>(src, (float*)dst, N, C, H * W, Cdst, c_off);
+    else
+        pu::nchw_to_nhwc_kernel<__nv_bfloat16><<<pu::grid_for(total), 256, 0, st>>>(src, (__nv_bfloat16*)dst, N, C,
+                                                                                  H * W, Cdst, c_off);
+    return pu::check_launch("nchw_to_nhwc");
+}
+
+int pu_nhwc_to_nchw(const void* src, float* dst, int N, int C, int H, int W, int src_dtype, void* stream) {
+    PU_REQUIRE(src && dst && N > 0 && C > 0 && H > 0 && W > 0, "pu_nhwc_to_nchw: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    long long total = (long long)N * C * H * W;
+    if (src_dtype == PU_F32)
+        pu::nhwc_to_nchw_kernel<float><<<pu::grid_for(total), 256, 0, st>>>((const float*)src, dst, N, C, H * W);
+    else
+        pu::nhwc_to_nchw_kernel<__nv_bfloat16><<<pu::grid_for(total), 256, 0, st>>>((const __nv_bfloat16*)src, dst, N,
+                                                                                  C, H * W);
+    return pu::check_launch("nhwc_to_nchw");
+}
+
+int pu_pack_conv_weight(const float* src, void* dst, int Co, int Ci, int k, int Ci_pad, int mode, const int* out_perm,
+                        long long src_co_stride, int dtype, void* stream) {
+    PU_REQUIRE(src && dst && Co > 0 && Ci > 0 && (k == 1 || k == 3) && Ci_pad >= Ci && (mode == 0 || mode == 1),
+               "pu_pack_conv_weight: bad arguments");
+    PU_REQUIRE(mode == 0 || Ci_pad == Ci, "pu_pack_conv_weight: dgrad packing takes no channel padding");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (src_co_stride <= 0) src_co_stride = (long long)Ci * k * k;
+    long long total = (mode == 0) ? (long long)Co * k * k * Ci_pad : (long long)Ci * k * k * Co;
+    if (dtype == PU_F32)
+        pu::pack_weight_kernel<float><<<pu::grid_for(total), 256, 0, st>>>(src, (float*)dst, Co, Ci, k, Ci_pad, mode,
+                                                                         out_perm, src_co_stride);
+    else
+        pu::pack_weight_kernel<__nv_bfloat16><<<pu::grid_for(total), 256, 0, st>>>(src, (__nv_bfloat16*)dst, Co, Ci, k,
+                                                                                 Ci_pad, mode, out_perm, src_co_stride);
+    return pu::check_launch("pack_conv_weight");
+}
+
+int pu_unpack_conv_wgrad(const float* src, float* dst, int Co, int Ci, int k, int Ci_pad, const int* out_perm,
+                         long long dst_co_stride, int accumulate, void* stream) {
+    PU_REQUIRE(src && dst && Co > 0 && Ci > 0 && (k == 1 || k == 3) && Ci_pad >= Ci, "pu_unpack_conv_wgrad: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dst_co_stride <= 0) dst_co_stride = (long long)Ci * k * k;
+    long long total = (long long)Co * Ci * k * k;
+    pu::unpack_wgrad_kernel<<<pu::grid_for(total), 256, 0, st>>>(src, dst, Co, Ci, k, Ci_pad, out_perm, accumulate,
+                                                                dst_co_stride);
+    return pu::check_launch("unpack_conv_wgrad");
+}
+
+int pu_gather_f32(const float* src, const int* perm, float* dst, int n, void* stream) {
+    PU_REQUIRE(src && perm && dst && n > 0, "pu_gather_f32: bad arguments");
+    pu::gather_kernel<<<pu::cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(src, perm, dst, n);
+    return pu::check_launch("gather_f32");
+}
+int pu_scatter_f32(const float* src, const int* perm, float* dst, int n, int accumulate, void* stream) {
+    PU_REQUIRE(src && perm && dst && n > 0, "pu_scatter_f32: bad arguments");
+    pu::scatter_kernel<<<pu::cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(src, perm, dst, n, accumulate);
+    return pu::check_launch("scatter_f32");
+}
+}

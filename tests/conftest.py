@@ -2,6 +2,11 @@ import os
 import sys
 
 import pytest
+import torch
+
+# references in the GPU tests must be true fp32 (torch defaults to TF32 convolutions on Ampere+)
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, 'tests', 'golden')):
@@ -11,3 +16,13 @@ for p in (ROOT, os.path.join(ROOT, 'tests', 'golden')):
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: test needs a CUDA device (run on the B200 box with -m gpu)')
+
+
+def pytest_collection_modifyitems(config, items):
+    import torch
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason='needs a CUDA device')
+    for item in items:
+        if 'gpu' in item.keywords:
+            item.add_marker(skip)

@@ -1,0 +1,35 @@
+"""CPU-side checks of the C ABI: the library builds/loads and exports every symbol include/*.h declares."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, 'include', 'probunet_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(pu_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from prob_unet_mds_b200 import _lib
+    from prob_unet_mds_b200 import build
+    path = build.build()
+    handle = ctypes.CDLL(path)
+    declared = _declared_symbols()
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(handle, name), f'{name} declared in include/probunet_b200.h but not exported'
+    # the ctypes binding covers exactly the declared ABI
+    assert sorted(_lib.exported_symbols()) == declared
+
+
+def test_error_reporting_without_gpu():
+    from prob_unet_mds_b200 import _lib
+    lib = _lib.lib()
+    assert lib.pu_version() >= 100
+    # argument validation happens before any CUDA call, so it can be exercised on a CPU-only box
+    rc = lib.pu_rsample(None, None, None, None, None, None, 0, None)
+    assert rc == -1
+    assert b'pu_rsample' in lib.pu_last_error()

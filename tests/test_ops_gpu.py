@@ -1,0 +1,451 @@
+"""Per-kernel parity tests through the C ABI against plain PyTorch fp32 references (GPU only)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from prob_unet_mds_b200 import _lib as L
+    from prob_unet_mds_b200 import ops
+
+DEV = 'cuda'
+
+
+def nhwc(x, dtype):
+    return x.permute(0, 2, 3, 1).contiguous().to(dtype)
+
+
+def nchw(x):
+    return x.permute(0, 3, 1, 2).float()
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def rel_err(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
+
+
+def max_err(a, b):
+    return (a.float() - b.float()).abs().max().item()
+
+
+def test_abi_loads_and_reports():
+    lib = L.lib()
+    assert lib.pu_version() >= 100
+    assert lib.pu_device_supports_tc() == 1, 'expected a compute-capability 10.x device (B200)'
+
+
+def test_layout_roundtrip():
+    x = rnd(2, 3, 8, 12)
+    for dt in (torch.float32, torch.bfloat16):
+        y = ops.nchw_to_nhwc(x, dt)
+        assert torch.equal(y, nhwc(x, dt))
+        back = ops.nhwc_to_nchw(y)
+        assert torch.equal(back, nhwc(x, dt).permute(0, 3, 1, 2).float())
+    cat = ops.nchw_to_nhwc(x, torch.float32, Cdst=8)
+    ops.nchw_to_nhwc(x, torch.float32, out=cat, c_off=3)
+    ref = torch.zeros(2, 8, 12, 8, device=DEV)
+    ref[..., :3] = x.permute(0, 2, 3, 1)
+    ref[..., 3:6] = x.permute(0, 2, 3, 1)
+    assert torch.equal(cat, ref)
+
+
+def test_pack_unpack():
+    w = rnd(8, 5, 3, 3)
+    p0 = ops.pack_weight(w, 0, torch.float32, Ci_pad=8)
+    ref0 = torch.zeros(8, 3, 3, 8, device=DEV)
+    ref0[..., :5] = w.permute(0, 2, 3, 1)
+    assert torch.equal(p0, ref0)
+    p1 = ops.pack_weight(w, 1, torch.float32)
+    ref1 = w.flip(2, 3).permute(1, 2, 3, 0).contiguous()
+    assert torch.equal(p1, ref1)
+    perm = torch.randperm(8).to(DEV).int()
+    pp = ops.pack_weight(w, 0, torch.float32, perm=perm)
+    assert torch.equal(pp, w[perm.long()].permute(0, 2, 3, 1).contiguous())
+    g = torch.zeros_like(w)
+    ops.unpack_wgrad(pp, g, perm=perm)
+    assert torch.equal(g, w)
+    ops.unpack_wgrad(pp, g, perm=perm, accumulate=True)
+    assert torch.equal(g, 2 * w)
+
+
+CONV_CASES = [
+    # N, H, W, C0, C1, Cout, k
+    (2, 16, 16, 64, 0, 64, 3),
+    (2, 32, 32, 128, 0, 256, 3),
+    (1, 16, 32, 64, 64, 192, 3),
+    (1, 24, 40, 128, 0, 128, 3),
+    (2, 16, 16, 256, 0, 768, 1),
+    (1, 16, 16, 128, 64, 128, 1),
+    (1, 64, 64, 64, 0, 128, 3),
+]
+
+
+def _conv_ref(x, w, b, res, relu):
+    y = F.conv2d(x, w, b, padding=w.shape[-1] // 2)
+    if res is not None:
+        y = y + res
+    return F.relu(y) if relu else y
+
+
+@pytest.mark.parametrize('case', CONV_CASES + [(2, 9, 7, 3, 0, 20, 3), (1, 5, 6, 6, 2, 10, 1)])
+@pytest.mark.parametrize('dtype', ['f32', 'bf16'])
+def test_conv_simple(case, dtype):
+    N, H, W, C0, C1, Co, k = case
+    dt = torch.float32 if dtype == 'f32' else torch.bfloat16
+    x = rnd(N, C0 + C1, H, W, seed=1).to(dt).float()
+    w = (rnd(Co, C0 + C1, k, k, seed=2) / math.sqrt((C0 + C1) * k * k)).to(dt).float()
+    b = rnd(Co, seed=3)
+    res = rnd(N, Co, H, W, seed=4).to(dt).float()
+    xs = nhwc(x, dt)
+    s0 = xs[..., :C0].contiguous()
+    s1 = xs[..., C0:].contiguous() if C1 else None
+    wp = ops.pack_weight(w, 0, dt)
+    y = ops.conv2d(s0, wp, Co, k, bias=b, src1=s1, residual=nhwc(res, dt), relu=True, flags=L.CONV_FORCE_SIMPLE)
+    ref = _conv_ref(x, w, b, res, True)
+    tol = 2e-5 if dtype == 'f32' else 1e-2
+    assert rel_err(nchw(y), ref) < tol
+
+
+@pytest.mark.parametrize('case', CONV_CASES)
+def test_conv_tc_fwd(case):
+    N, H, W, C0, C1, Co, k = case
+    dt = torch.bfloat16
+    x = rnd(N, C0 + C1, H, W, seed=1).to(dt).float()
+    w = (rnd(Co, C0 + C1, k, k, seed=2) / math.sqrt((C0 + C1) * k * k)).to(dt).float()
+    b = rnd(Co, seed=3)
+    res = rnd(N, Co, H, W, seed=4).to(dt).float()
+    xs = nhwc(x, dt)
+    s0 = xs[..., :C0].contiguous()
+    s1 = xs[..., C0:].contiguous() if C1 else None
+    wp = ops.pack_weight(w, 0, dt)
+    # plain conv first (no epilogue extras), then the full epilogue
+    y0 = ops.conv2d(s0, wp, Co, k, src1=s1, flags=L.CONV_FORCE_TC)
+    ref0 = F.conv2d(x, w, None, padding=k // 2)
+    e0 = rel_err(nchw(y0), ref0)
+    y = ops.conv2d(s0, wp, Co, k, bias=b, src1=s1, residual=nhwc(res, dt), relu=True, flags=L.CONV_FORCE_TC)
+    ref = _conv_ref(x, w, b, res, True)
+    e1 = rel_err(nchw(y), ref)
+    print(f'conv_tc {case}: plain rel {e0:.3e}, epilogue rel {e1:.3e}, max {max_err(nchw(y), ref):.3e}')
+    assert e0 < 6e-3 and e1 < 6e-3
+
+
+@pytest.mark.parametrize('case', CONV_CASES)
+@pytest.mark.parametrize('impl', ['simple_f32', 'tc'])
+def test_conv_dgrad(case, impl):
+    N, H, W, C0, C1, Co, k = case
+    dt = torch.float32 if impl == 'simple_f32' else torch.bfloat16
+    Ci = C0 + C1
+    w = (rnd(Co, Ci, k, k, seed=2) / math.sqrt(Ci * k * k)).to(dt).float()
+    dy = rnd(N, Co, H, W, seed=5).to(dt).float()
+    x = torch.zeros(N, Ci, H, W, device=DEV, requires_grad=True)
+    F.conv2d(x, w, padding=k // 2).backward(dy)
+    wp = ops.pack_weight(w, 1, dt)
+    flags = L.CONV_FORCE_SIMPLE if impl == 'simple_f32' else L.CONV_FORCE_TC
+    dx = ops.conv2d(nhwc(dy, dt), wp, Ci, k, flags=flags)
+    e = rel_err(nchw(dx), x.grad)
+    print(f'dgrad {impl} {case}: rel {e:.3e}')
+    assert e < (2e-5 if impl == 'simple_f32' else 6e-3)
+
+
+@pytest.mark.parametrize('case', CONV_CASES + [(2, 9, 7, 3, 0, 20, 3)])
+@pytest.mark.parametrize('impl', ['simple_f32', 'simple_bf16', 'tc'])
+def test_conv_wgrad(case, impl):
+    N, H, W, C0, C1, Co, k = case
+    if impl == 'tc' and (C0 % 64 or Co % 64):
+        pytest.skip('tc needs 64-multiples')
+    dt = torch.float32 if impl == 'simple_f32' else torch.bfloat16
+    Ci = C0 + C1
+    x = rnd(N, Ci, H, W, seed=1).to(dt).float()
+    dy = rnd(N, Co, H, W, seed=5).to(dt).float()
+    w = torch.zeros(Co, Ci, k, k, device=DEV, requires_grad=True)
+    F.conv2d(x, w, padding=k // 2).backward(dy)
+    xs = nhwc(x, dt)
+    s0 = xs[..., :C0].contiguous()
+    s1 = xs[..., C0:].contiguous() if C1 else None
+    flags = L.CONV_FORCE_TC if impl == 'tc' else L.CONV_FORCE_SIMPLE
+    dwp = ops.conv2d_wgrad(s0, nhwc(dy, dt), k, src1=s1, flags=flags)
+    g = torch.empty_like(w)
+    ops.unpack_wgrad(dwp, g)
+    e = rel_err(g, w.grad)
+    print(f'wgrad {impl} {case}: rel {e:.3e}')
+    assert e < (2e-5 if impl == 'simple_f32' else 2e-3)
+    db = ops.bias_grad(nhwc(dy, dt))
+    assert rel_err(db, dy.sum(dim=(0, 2, 3))) < 1e-5
+
+
+GN_CASES = [
+    # N, H, W, C0, C1, silu, ada, resample, dropout
+    (2, 8, 8, 128, 0, True, False, 0, 0.0),
+    (2, 8, 8, 128, 0, True, True, 0, 0.0),
+    (1, 8, 12, 256, 128, True, True, 0, 0.0),
+    (2, 8, 8, 512, 384, True, False, 0, 0.0),
+    (2, 8, 8, 128, 0, True, False, 1, 0.0),
+    (2, 8, 8, 128, 0, True, False, 2, 0.0),
+    (2, 8, 8, 256, 0, False, False, 0, 0.0),
+    (1, 16, 16, 64, 0, True, True, 0, 0.0),
+]
+
+
+def _gn_ref(x, gamma, beta, ada, silu, resample):
+    Cc = x.shape[1]
+    y = F.group_norm(x, min(32, Cc // 4), gamma, beta, 1e-5)
+    if ada is not None:
+        y = torch.addcmul(ada[Cc:].view(1, -1, 1, 1), y, ada[:Cc].view(1, -1, 1, 1) + 1)
+    if silu:
+        y = F.silu(y)
+    if resample == 1:
+        y = F.interpolate(y, scale_factor=2, mode='nearest')
+    elif resample == 2:
+        y = F.avg_pool2d(y, 2)
+    return y
+
+
+@pytest.mark.parametrize('case', GN_CASES)
+@pytest.mark.parametrize('dtype', ['f32', 'bf16'])
+def test_groupnorm_fwd_bwd(case, dtype):
+    N, H, W, C0, C1, silu, use_ada, rs, p = case
+    dt = torch.float32 if dtype == 'f32' else torch.bfloat16
+    Cc = C0 + C1
+    x = (rnd(N, Cc, H, W, seed=1) * 1.5 + 0.3).to(dt).float().requires_grad_(True)
+    gamma = (1 + 0.1 * rnd(Cc, seed=2)).requires_grad_(True)
+    beta = (0.1 * rnd(Cc, seed=3)).requires_grad_(True)
+    ada = (0.1 * rnd(2 * Cc, seed=4)).requires_grad_(True) if use_ada else None
+    y_ref = _gn_ref(x, gamma, beta, ada, silu, rs)
+    dy = rnd(*y_ref.shape, seed=5).to(dt).float()
+    dres = rnd(N, Cc, H, W, seed=6).to(dt).float()
+    y_ref.backward(dy)
+
+    xs = nhwc(x.detach(), dt)
+    s0 = xs[..., :C0].contiguous()
+    s1 = xs[..., C0:].contiguous() if C1 else None
+    stats = ops.gn_stats(s0, s1)
+    G = min(32, Cc // 4)
+    xg = x.detach().reshape(N, G, -1).double()
+    assert torch.allclose(stats[..., 0], xg.sum(-1), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(stats[..., 1], (xg * xg).sum(-1), rtol=1e-5, atol=1e-3)
+    y = ops.gn_apply(s0, stats, gamma.detach(), beta.detach(), src1=s1, ada=ada.detach() if use_ada else None,
+                     silu=silu, resample=rs)
+    tol = 1e-5 if dtype == 'f32' else 6e-3
+    assert rel_err(nchw(y), y_ref) < tol
+
+    dgamma = torch.empty(Cc, device=DEV)
+    dbeta = torch.empty(Cc, device=DEV)
+    dada = torch.empty(2 * Cc, device=DEV) if use_ada else None
+    dx0, dx1 = ops.gn_bwd(s0, stats, gamma.detach(), beta.detach(), nhwc(dy, dt), dgamma, dbeta, src1=s1,
+                          ada=ada.detach() if use_ada else None, dada=dada, silu=silu, resample=rs,
+                          dres=nhwc(dres, dt))
+    dx = torch.cat([dx0, dx1], dim=-1) if C1 else dx0
+    btol = 2e-4 if dtype == 'f32' else 1.5e-2
+    assert rel_err(nchw(dx), x.grad + dres) < btol
+    assert rel_err(dgamma, gamma.grad) < btol
+    assert rel_err(dbeta, beta.grad) < btol
+    if use_ada:
+        assert rel_err(dada, ada.grad) < btol
+
+
+def test_groupnorm_dropout_consistency():
+    N, H, W, Cc = 2, 8, 8, 128
+    x = nhwc(rnd(N, Cc, H, W, seed=1), torch.float32)
+    gamma = torch.ones(Cc, device=DEV)
+    beta = torch.zeros(Cc, device=DEV)
+    stats = ops.gn_stats(x)
+    y0 = ops.gn_apply(x, stats, gamma, beta, silu=True)
+    y = ops.gn_apply(x, stats, gamma, beta, silu=True, dropout_p=0.1, seed=1234)
+    kept = y != 0
+    frac = kept.float().mean().item()
+    assert 0.85 < frac < 0.95
+    assert torch.allclose(y[kept], y0[kept] / 0.9, rtol=1e-6)
+    y2 = ops.gn_apply(x, stats, gamma, beta, silu=True, dropout_p=0.1, seed=1234)
+    assert torch.equal(y, y2)
+    # backward uses the same mask: dx of dropped elements only gets the group-mean terms; check via linearity
+    dy = torch.ones_like(x)
+    dg = torch.empty(Cc, device=DEV)
+    db = torch.empty(Cc, device=DEV)
+    ops.gn_bwd(x, stats, gamma, beta, dy, dg, db, silu=True, dropout_p=0.1, seed=1234)
+    # d beta = sum over kept elements of dsilu(u) / 0.9
+    u = (x - (stats[..., 0] / (Cc // 32 * H * W)).float().repeat_interleave(Cc // 32, 1)[:, None, None, :])
+    var = (stats[..., 1] / (Cc // 32 * H * W) - (stats[..., 0] / (Cc // 32 * H * W)) ** 2).float()
+    u = u * torch.rsqrt(var + 1e-5).repeat_interleave(Cc // 32, 1)[:, None, None, :]
+    s = torch.sigmoid(u)
+    ds = s * (1 + u * (1 - s))
+    ref_db = (ds * kept / 0.9).sum(dim=(0, 1, 2))
+    assert rel_err(db, ref_db) < 1e-4
+
+
+def _attn_ref(qkv_my, heads):
+    # qkv_my: [N, T, 3C] in (j, head, d) order, fp32
+    N, T, C3 = qkv_my.shape
+    Cc = C3 // 3
+    q, k, v = [t.reshape(N, T, heads, 64).permute(0, 2, 1, 3) for t in qkv_my.split(Cc, dim=-1)]
+    w = torch.softmax(q @ k.transpose(-1, -2) / 8.0, dim=-1)
+    return (w @ v).permute(0, 2, 1, 3).reshape(N, T, Cc)
+
+
+@pytest.mark.parametrize('N,T,heads', [(2, 64, 2), (1, 100, 4), (2, 256, 4)])
+@pytest.mark.parametrize('dtype', ['f32', 'bf16'])
+def test_attention_simple(N, T, heads, dtype):
+    dt = torch.float32 if dtype == 'f32' else torch.bfloat16
+    Cc = heads * 64
+    qkv = rnd(N, T, 3 * Cc, seed=1).to(dt).float().requires_grad_(True)
+    ref = _attn_ref(qkv, heads)
+    dout = rnd(N, T, Cc, seed=2).to(dt).float()
+    ref.backward(dout)
+    out, lse = ops.attention_fwd(qkv.detach().to(dt), heads, flags=L.CONV_FORCE_SIMPLE)
+    tol = 1e-5 if dtype == 'f32' else 6e-3
+    assert rel_err(out, ref) < tol
+    dqkv = ops.attention_bwd(qkv.detach().to(dt), out, dout.to(dt), lse, heads, flags=L.CONV_FORCE_SIMPLE)
+    assert rel_err(dqkv, qkv.grad) < (1e-4 if dtype == 'f32' else 1.5e-2)
+
+
+def test_encoder_glue():
+    x = rnd(2, 64, 8, 8, seed=1)
+    xs = nhwc(x, torch.float32)
+    assert torch.allclose(nchw(ops.avgpool2(xs)), F.avg_pool2d(x, 2), atol=1e-6)
+    assert torch.equal(nchw(ops.upsample2(xs)), F.interpolate(x, scale_factor=2, mode='nearest'))
+    xb = nhwc(x, torch.bfloat16)
+    assert torch.equal(nchw(ops.upsample2(xb)), F.interpolate(xb.permute(0, 3, 1, 2).float(), scale_factor=2, mode='nearest'))
+    m = ops.global_mean(xs)
+    assert torch.allclose(m, x.mean(dim=(2, 3)), atol=1e-6)
+    r = F.relu(x)
+    dp = rnd(2, 64, 4, 4, seed=2)
+    rr = r.clone().requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    F.avg_pool2d(F.relu(xr), 2).backward(dp)
+    dr = ops.relu_pool_bwd(nhwc(dp, torch.float32), nhwc(r, torch.float32))
+    assert torch.allclose(nchw(dr), xr.grad, atol=1e-6)
+    dm = rnd(2, 64, seed=3)
+    xr2 = x.clone().requires_grad_(True)
+    F.relu(xr2).mean(dim=(2, 3)).backward(dm)
+    dr2 = ops.relu_mean_bwd(dm, nhwc(r, torch.float32))
+    assert torch.allclose(nchw(dr2), xr2.grad, atol=1e-7)
+    g = rnd(2, 64, 8, 8, seed=4)
+    assert torch.equal(nchw(ops.relu_mask(nhwc(g, torch.float32), nhwc(r, torch.float32))), g * (r > 0))
+
+
+def test_heads_rsample_kl_mse():
+    N, Cc, Lz = 4, 512, 16
+    m = rnd(N, Cc, seed=1).requires_grad_(True)
+    w = (rnd(2 * Lz, Cc, seed=2) / math.sqrt(Cc)).requires_grad_(True)
+    b = rnd(2 * Lz, seed=3).requires_grad_(True)
+    ref = m @ w.t() + b
+    out = ops.heads_fwd(m.detach(), w.detach(), b.detach())
+    assert torch.allclose(out, ref, rtol=1e-5, atol=1e-5)
+    dout = rnd(N, 2 * Lz, seed=4)
+    ref.backward(dout)
+    dw = torch.empty_like(w)
+    db = torch.empty_like(b)
+    dm = ops.heads_bwd(m.detach(), w.detach(), dout, dw, db)
+    assert torch.allclose(dm, m.grad, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(dw, w.grad, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(db, b.grad, rtol=1e-5, atol=1e-5)
+
+    mu_q = rnd(N, Lz, seed=5).requires_grad_(True)
+    ls_q = (0.3 * rnd(N, Lz, seed=6)).requires_grad_(True)
+    mu_p = rnd(N, Lz, seed=7).requires_grad_(True)
+    ls_p = (0.3 * rnd(N, Lz, seed=8)).requires_grad_(True)
+    eps = rnd(N, Lz, seed=9)
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    z, sigma = ops.rsample(mu_q.detach(), ls_q.detach(), eps, flag)
+    # bit-exact given the same (mu, sigma, eps): torch's Normal.rsample is loc + eps * scale
+    assert torch.equal(z, mu_q.detach() + eps * sigma)
+    assert torch.allclose(sigma, torch.exp(ls_q.detach()), rtol=2e-7)
+    assert flag.item() == 0
+    bad = mu_q.detach().clone()
+    bad[0, 0] = float('nan')
+    ops.rsample(bad, ls_q.detach(), eps, flag)
+    assert flag.item() == 1
+
+    from torch.distributions import Independent, Normal, kl
+    q = Independent(Normal(mu_q, torch.exp(ls_q)), 1)
+    p = Independent(Normal(mu_p, torch.exp(ls_p)), 1)
+    ref_kl = kl.kl_divergence(q, p).sum()
+    ref_kl.backward()
+    acc = torch.zeros(2, dtype=torch.float64, device=DEV)
+    g = ops.kl_fwd_bwd(mu_q.detach(), ls_q.detach(), mu_p.detach(), ls_p.detach(), acc[1:])
+    assert abs(acc[1].item() - ref_kl.item()) < 1e-5 * abs(ref_kl.item())
+    for got, want in zip(g, (mu_q.grad, ls_q.grad, mu_p.grad, ls_p.grad)):
+        assert torch.allclose(got, want, rtol=1e-4, atol=1e-5)
+
+    o = rnd(2, 3, 8, 8, seed=10)
+    t = rnd(2, 3, 8, 8, seed=11)
+    dl = ops.mse_fwd_bwd(o, t, acc[:1], dtype=torch.float32)
+    assert abs(acc[0].item() - ((o - t) ** 2).sum().item()) < 1e-5 * acc[0].item()
+    assert torch.allclose(nchw(dl), 2 * (o - t), atol=1e-6)
+    total, recon, klv = ops.loss_finalize(acc, 0.5)
+    assert abs(total.item() - (acc[0].item() + 0.5 * acc[1].item())) < 1e-3
+    assert abs(recon.item() - acc[0].item()) < 1e-3 and abs(klv.item() - acc[1].item()) < 1e-5
+    sc = ops.loss_bwd_scales(torch.tensor(2.0, device=DEV), None, torch.tensor(0.25, device=DEV), 0.5, DEV)
+    assert torch.allclose(sc, torch.tensor([2.0, 1.25], device=DEV))
+    g2 = ops.kl_fwd_bwd(mu_q.detach(), ls_q.detach(), mu_p.detach(), ls_p.detach(), acc[1:], gscale=sc[1:])
+    assert torch.allclose(g2[0], 1.25 * mu_q.grad, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize('dtype', ['f32', 'bf16'])
+@pytest.mark.parametrize('S', [1, 3])
+def test_fcomb_fwd(dtype, S):
+    dt = torch.float32 if dtype == 'f32' else torch.bfloat16
+    N, H, W, Lz = 2, 16, 12, 6
+    feat = rnd(N, 64, H, W, seed=1).to(dt).float()
+    z = rnd(N, S, Lz, seed=2)
+    w0 = rnd(64, 64 + Lz, 1, 1, seed=3) / 8
+    b0 = rnd(64, seed=4) * 0.1
+    w1 = rnd(64, 64, 1, 1, seed=5) / 8
+    b1 = rnd(64, seed=6) * 0.1
+    w2 = rnd(3, 64, 1, 1, seed=7) / 8
+    b2 = rnd(3, seed=8) * 0.1
+    out, h1, h2 = ops.fcomb_fwd(nhwc(feat, dt), z if S > 1 else z[:, 0].contiguous(), w0, b0, w1, b1, w2, b2, S=S,
+                                save_hidden=(S == 1))
+    for s in range(S):
+        zt = z[:, s, :, None, None].expand(-1, -1, H, W)
+        h = F.relu(F.conv2d(torch.cat([feat, zt], 1), w0, b0))
+        hh = F.relu(F.conv2d(h, w1, b1))
+        ref = F.conv2d(hh, w2, b2)
+        got = out[:, s] if S > 1 else out
+        assert rel_err(got, ref) < 1e-5
+        if S == 1:
+            assert rel_err(nchw(h1), h) < (1e-5 if dtype == 'f32' else 4e-3)
+            assert rel_err(nchw(h2), hh) < (1e-5 if dtype == 'f32' else 4e-3)
+
+
+def test_fcomb_z_bwd_and_rsample_bwd():
+    N, Lz = 3, 6
+    rmean = rnd(N, 64, seed=1)
+    z = rnd(N, Lz, seed=2)
+    w0 = rnd(64, 64 + Lz, seed=3)
+    dw0 = torch.zeros_like(w0)
+    db0 = torch.zeros(64, device=DEV)
+    hw = 96.0
+    dz = ops.fcomb_z_bwd(rmean, hw, z, w0, dw0, db0)
+    R = rmean * hw
+    assert torch.allclose(dz, R @ w0[:, 64:], rtol=1e-5, atol=1e-4)
+    assert torch.allclose(dw0[:, 64:], R.t() @ z, rtol=1e-5, atol=1e-4)
+    assert torch.equal(dw0[:, :64], torch.zeros(64, 64, device=DEV))
+    assert torch.allclose(db0, R.sum(0), rtol=1e-5, atol=1e-4)
+    eps = rnd(N, Lz, seed=4)
+    sigma = rnd(N, Lz, seed=5).abs()
+    dmu = torch.ones(N, Lz, device=DEV)
+    dls = torch.ones(N, Lz, device=DEV)
+    ops.rsample_bwd(dz, eps, sigma, dmu, dls)
+    assert torch.allclose(dmu, 1 + dz)
+    assert torch.allclose(dls, 1 + dz * eps * sigma, rtol=1e-6)
+
+
+def test_adamw_matches_torch():
+    p = rnd(1000, seed=1)
+    ref = torch.nn.Parameter(p.clone())
+    opt = torch.optim.AdamW([ref], lr=1e-3)
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    for step in range(1, 4):
+        g = rnd(1000, seed=10 + step)
+        ref.grad = g.clone()
+        opt.step()
+        ops.adamw_step(p, g, m, v, 1e-3, 0.9, 0.999, 1e-8, 0.01, step)
+        assert torch.allclose(p, ref.detach(), rtol=1e-5, atol=1e-7)
