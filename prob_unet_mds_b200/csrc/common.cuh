@@ -77,6 +77,8 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&v)[8]) {
     *reinterpret_cast<uint4*>(p) = r;
 }
 
+// ReLU that propagates NaN like torch.relu (fmaxf would swallow it and hide invalid inputs from the validate flag)
+__device__ __forceinline__ float relu_f(float v) { return v < 0.f ? 0.f : v; }
 __device__ __forceinline__ float silu_f(float u) { return u / (1.0f + expf(-u)); }
 // d silu(u) / du
 __device__ __forceinline__ float dsilu_f(float u) {

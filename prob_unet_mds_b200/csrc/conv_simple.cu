@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(256) conv_simple_kernel(PuConvArgs a) {
             float v = acc[i][j];
             if (a.bias) v += a.bias_per_sample ? a.bias[(long long)img * a.Cout + n] : a.bias[n];
             if (res) v += ldf(res + m * a.Cout + n);
-            if (a.flags & PU_CONV_RELU) v = fmaxf(v, 0.f);
+            if (a.flags & PU_CONV_RELU) v = relu_f(v);
             stf(out + m * a.Cout + n, v);
         }
     }

@@ -291,7 +291,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     }
                     if (p.relu) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                        for (int j = 0; j < 32; ++j) f[j] = relu_f(f[j]);
                     }
                     __nv_bfloat16* op = p.out + pix * p.Cout + n0 + c;
 #pragma unroll

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(128) fcomb_fwd_kernel(PuFcombArgs a) {
         __syncthreads();
         float h1[FC];
 #pragma unroll
-        for (int o = 0; o < FC; ++o) h1[o] = fmaxf(pre[o] + zb[o], 0.f);
+        for (int o = 0; o < FC; ++o) h1[o] = relu_f(pre[o] + zb[o]);
         if (a.h1_out && valid) {
             T* hp = reinterpret_cast<T*>(a.h1_out) + ((long long)n * a.HW + p) * FC;
 #pragma unroll
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(128) fcomb_fwd_kernel(PuFcombArgs a) {
                     acc = fmaf(w.z, h1[i4 * 4 + 2], acc);
                     acc = fmaf(w.w, h1[i4 * 4 + 3], acc);
                 }
-                const float r = fmaxf(acc, 0.f);
+                const float r = relu_f(acc);
                 r8[e] = r;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) out[c] = fmaf(w2[c][o2], r, out[c]);

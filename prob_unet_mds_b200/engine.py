@@ -1,0 +1,389 @@
+"""Forward / hand-derived backward execution of the U-Net, the Gaussian encoders and Fcomb over the C ABI.
+
+Nothing here computes with torch: torch allocates buffers (torch.empty), owns the parameters and the RNG, and
+wires the result into autograd through two torch.autograd.Function classes (one per public entry point).
+Every arithmetic step is a pu_* kernel launch (prob_unet_mds_b200/ops.py).
+
+Data layout in HBM: activations NHWC in the compute dtype (bf16 by default, fp32 in "fp32 mode"); conv weights
+are re-packed from the fp32 OIHW master parameters into [Cout][kh][kw][Cin] (forward) and [Cin][kh][kw][Cout]
+(flipped, data-gradient) whenever a parameter's version counter changes; parameter gradients are fp32.
+"""
+import os
+
+import torch
+
+from . import _lib as L
+from . import ops
+
+
+def default_compute_dtype():
+    v = os.environ.get('PROBUNET_B200_DTYPE', 'bf16').lower()
+    if v in ('bf16', 'bfloat16'):
+        return torch.bfloat16
+    if v in ('fp32', 'f32', 'float32'):
+        return torch.float32
+    raise ValueError(f'PROBUNET_B200_DTYPE={v!r}: expected bf16 or fp32')
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(f'probunet_b200: {what} must live on a CUDA device (there is no CPU path); got {t.device}')
+
+
+class _PackCache:
+    """Packed copies of parameters, refreshed when the parameter is modified in place (optimizer step) or moved."""
+
+    def __init__(self):
+        self._store = {}
+
+    def get(self, key, param, make):
+        tag = (param._version, param.data_ptr())
+        hit = self._store.get(key)
+        if hit is not None and hit[0] == tag:
+            return hit[1]
+        val = make()
+        self._store[key] = (tag, val)
+        return val
+
+
+# ======================================================================================================================
+# U-Net
+# ======================================================================================================================
+class UNetEngine:
+    def __init__(self, unet, dtype):
+        self.unet = unet
+        self.dtype = dtype
+        self.cache = _PackCache()
+        self._perms = {}
+        self._step = 0
+
+    # ---- packed parameters ------------------------------------------------------------------------------------------
+    def w_fwd(self, p, perm=None):
+        return self.cache.get((id(p), 'f', self.dtype), p, lambda: ops.pack_weight(p.detach(), 0, self.dtype, perm=perm))
+
+    def w_dgrad(self, p, perm=None):
+        return self.cache.get((id(p), 'd', self.dtype), p, lambda: ops.pack_weight(p.detach(), 1, self.dtype, perm=perm))
+
+    def qkv_perm(self, C, heads, device):
+        """my channel (j, head, d) -> reference channel head*192 + d*3 + j  (networks.py:180 reshape/unbind)."""
+        key = (C, heads, str(device))
+        if key not in self._perms:
+            idx = []
+            for j in range(3):
+                for h in range(heads):
+                    for d in range(64):
+                        idx.append(h * 192 + d * 3 + j)
+            self._perms[key] = torch.tensor(idx, dtype=torch.int32).to(device)
+        return self._perms[key]
+
+    def bias_perm(self, p, perm):
+        return self.cache.get((id(p), 'bp'), p, lambda: ops.gather(p.detach(), perm))
+
+    # ---- forward ----------------------------------------------------------------------------------------------------
+    def forward(self, x, training, save, seed_base=0):
+        """x: NHWC [N,H,W,in_channels] in self.dtype.  Returns (features NHWC, tape or None)."""
+        u = self.unet
+        tape = [] if save else None
+        skips = []
+        bi = 0
+        for name, mod in u.enc.items():
+            if isinstance(mod, torch.nn.Module) and hasattr(mod, 'norm0'):
+                x, rec = self._block_fwd(mod, x, None, training, seed_base + bi, save)
+                bi += 1
+            else:
+                xin = x
+                x = ops.conv2d(xin, self.w_fwd(mod.weight), mod.out_channels, mod.kernel, bias=mod.bias)
+                rec = dict(kind='conv', mod=mod, xin=xin, out=x)
+            if save:
+                tape.append(rec)
+            skips.append(x)
+        for name, mod in u.dec.items():
+            xb = None
+            if x.shape[3] != mod.in_channels:
+                xb = skips.pop()
+            x, rec = self._block_fwd(mod, x, xb, training, seed_base + bi, save)
+            bi += 1
+            if save:
+                tape.append(rec)
+        st = ops.gn_stats(x)
+        h = ops.gn_apply(x, st, u.out_norm.weight, u.out_norm.bias, silu=True, eps=u.out_norm.eps)
+        feat = ops.conv2d(h, self.w_fwd(u.out_conv.weight), u.out_conv.out_channels, 3, bias=u.out_conv.bias)
+        if save:
+            tape.append(dict(kind='out', x=x, st=st, h=h, out=feat))
+        return feat, tape
+
+    def _block_fwd(self, blk, xa, xb, training, seed, save):
+        Cout = blk.out_channels
+        rs = L.RS_UP if blk.up else (L.RS_DOWN if blk.down else L.RS_NONE)
+        st0 = ops.gn_stats(xa, xb)
+        h0 = ops.gn_apply(xa, st0, blk.norm0.weight, blk.norm0.bias, src1=xb, silu=True, resample=rs, eps=blk.norm0.eps)
+        a = ops.conv2d(h0, self.w_fwd(blk.conv0.weight), Cout, 3, bias=blk.conv0.bias)
+        st1 = ops.gn_stats(a)
+        p = float(blk.dropout) if training else 0.0
+        h1 = ops.gn_apply(a, st1, blk.norm1.weight, blk.norm1.bias, ada=blk.affine.bias, silu=True, dropout_p=p,
+                          seed=seed, eps=blk.norm1.eps)
+        w1 = self.w_fwd(blk.conv1.weight)
+        if blk.skip is not None and blk.skip.weight is not None:
+            if blk.up or blk.down:
+                raise NotImplementedError('resampling 1x1 skip (resample_proj) is not on the path')
+            s = ops.conv2d(xa, self.w_fwd(blk.skip.weight), Cout, 1, bias=blk.skip.bias, src1=xb)
+            y = ops.conv2d(h1, w1, Cout, 3, bias=blk.conv1.bias, residual=s, out=s)
+        elif blk.up:
+            s = ops.upsample2(xa)
+            y = ops.conv2d(h1, w1, Cout, 3, bias=blk.conv1.bias, residual=s, out=s)
+        elif blk.down:
+            s = ops.avgpool2(xa)
+            y = ops.conv2d(h1, w1, Cout, 3, bias=blk.conv1.bias, residual=s, out=s)
+        else:
+            y = ops.conv2d(h1, w1, Cout, 3, bias=blk.conv1.bias, residual=xa)
+        rec = None
+        if save:
+            rec = dict(kind='block', blk=blk, xa=xa, xb=xb, st0=st0, h0=h0, a=a, st1=st1, h1=h1, y=y, p=p, seed=seed,
+                       rs=rs)
+        out = y
+        if blk.num_heads:
+            heads = blk.num_heads
+            perm = self.qkv_perm(Cout, heads, y.device)
+            st2 = ops.gn_stats(y)
+            h2 = ops.gn_apply(y, st2, blk.norm2.weight, blk.norm2.bias, silu=False, eps=blk.norm2.eps)
+            qkv = ops.conv2d(h2, self.w_fwd(blk.qkv.weight, perm), 3 * Cout, 1, bias=self.bias_perm(blk.qkv.bias, perm))
+            att, lse = ops.attention_fwd(qkv, heads)
+            out = ops.conv2d(att, self.w_fwd(blk.proj.weight), Cout, 1, bias=blk.proj.bias, residual=y)
+            if save:
+                rec.update(st2=st2, h2=h2, qkv=qkv, att=att, lse=lse, perm=perm)
+        if save:
+            rec['out'] = out
+        return out, rec
+
+    # ---- backward ---------------------------------------------------------------------------------------------------
+    def _wgrad(self, grads, param, src0, dy, k, src1=None, perm=None):
+        dwp = ops.conv2d_wgrad(src0, dy, k, src1=src1)
+        g = torch.empty_like(param)
+        ops.unpack_wgrad(dwp, g, perm=perm)
+        grads[id(param)] = g
+
+    def backward(self, tape, dfeat, grads):
+        """dfeat: NHWC gradient wrt the features.  Fills grads[id(param)] for every live parameter."""
+        u = self.unet
+        gbuf = {}   # id(activation tensor) -> gradient tensor accumulated so far
+
+        rec = tape[-1]
+        self._wgrad(grads, u.out_conv.weight, rec['h'], dfeat, 3)
+        grads[id(u.out_conv.bias)] = ops.bias_grad(dfeat)
+        dh = ops.conv2d(dfeat, self.w_dgrad(u.out_conv.weight), rec['h'].shape[3], 3)
+        dg = torch.empty_like(u.out_norm.weight)
+        db = torch.empty_like(u.out_norm.bias)
+        dx, _ = ops.gn_bwd(rec['x'], rec['st'], u.out_norm.weight, u.out_norm.bias, dh, dg, db, silu=True,
+                           eps=u.out_norm.eps)
+        grads[id(u.out_norm.weight)] = dg
+        grads[id(u.out_norm.bias)] = db
+        gbuf[id(rec['x'])] = dx
+
+        for rec in reversed(tape[:-1]):
+            dout = gbuf.pop(id(rec['out']))
+            if rec['kind'] == 'conv':
+                mod = rec['mod']
+                self._wgrad(grads, mod.weight, rec['xin'], dout, mod.kernel)
+                grads[id(mod.bias)] = ops.bias_grad(dout)
+                continue
+            self._block_bwd(rec, dout, grads, gbuf)
+        return grads
+
+    def _block_bwd(self, rec, dz, grads, gbuf):
+        blk = rec['blk']
+        Cout = blk.out_channels
+        xa, xb = rec['xa'], rec['xb']
+        Cin = xa.shape[3] + (xb.shape[3] if xb is not None else 0)
+        if blk.num_heads:
+            heads = blk.num_heads
+            perm = rec['perm']
+            self._wgrad(grads, blk.proj.weight, rec['att'], dz, 1)
+            grads[id(blk.proj.bias)] = ops.bias_grad(dz)
+            datt = ops.conv2d(dz, self.w_dgrad(blk.proj.weight), Cout, 1)
+            dqkv = ops.attention_bwd(rec['qkv'], rec['att'], datt, rec['lse'], heads)
+            self._wgrad(grads, blk.qkv.weight, rec['h2'], dqkv, 1, perm=perm)
+            dbq = ops.bias_grad(dqkv)
+            gq = torch.empty_like(blk.qkv.bias)
+            ops.scatter(dbq, perm, gq)
+            grads[id(blk.qkv.bias)] = gq
+            dh2 = ops.conv2d(dqkv, self.w_dgrad(blk.qkv.weight, perm), Cout, 1)
+            dg = torch.empty_like(blk.norm2.weight)
+            db = torch.empty_like(blk.norm2.bias)
+            dy, _ = ops.gn_bwd(rec['y'], rec['st2'], blk.norm2.weight, blk.norm2.bias, dh2, dg, db, silu=False,
+                               eps=blk.norm2.eps, dres=dz)
+            grads[id(blk.norm2.weight)] = dg
+            grads[id(blk.norm2.bias)] = db
+        else:
+            dy = dz
+        # conv1
+        self._wgrad(grads, blk.conv1.weight, rec['h1'], dy, 3)
+        grads[id(blk.conv1.bias)] = ops.bias_grad(dy)
+        dh1 = ops.conv2d(dy, self.w_dgrad(blk.conv1.weight), Cout, 3)
+        dg = torch.empty_like(blk.norm1.weight)
+        db = torch.empty_like(blk.norm1.bias)
+        dada = torch.empty_like(blk.affine.bias)
+        da, _ = ops.gn_bwd(rec['a'], rec['st1'], blk.norm1.weight, blk.norm1.bias, dh1, dg, db, ada=blk.affine.bias,
+                           dada=dada, silu=True, dropout_p=rec['p'], seed=rec['seed'], eps=blk.norm1.eps)
+        grads[id(blk.norm1.weight)] = dg
+        grads[id(blk.norm1.bias)] = db
+        grads[id(blk.affine.bias)] = dada
+        # conv0
+        self._wgrad(grads, blk.conv0.weight, rec['h0'], da, 3)
+        grads[id(blk.conv0.bias)] = ops.bias_grad(da)
+        dh0 = ops.conv2d(da, self.w_dgrad(blk.conv0.weight), Cin, 3)
+        # skip branch
+        rs = rec['rs']
+        if blk.skip is not None and blk.skip.weight is not None:
+            self._wgrad(grads, blk.skip.weight, xa, dy, 1, src1=xb)
+            grads[id(blk.skip.bias)] = ops.bias_grad(dy)
+            dres = ops.conv2d(dy, self.w_dgrad(blk.skip.weight), Cin, 1)
+            dres_rs = L.RS_NONE
+        else:
+            dres = dy
+            dres_rs = rs
+        dg = torch.empty_like(blk.norm0.weight)
+        db = torch.empty_like(blk.norm0.bias)
+        ga = gbuf.get(id(xa))
+        gb = gbuf.get(id(xb)) if xb is not None else None
+        dxa, dxb = ops.gn_bwd(xa, rec['st0'], blk.norm0.weight, blk.norm0.bias, dh0, dg, db, src1=xb, silu=True,
+                              resample=rs, eps=blk.norm0.eps, dres=dres, dres_resample=dres_rs,
+                              dx0=ga, dx1=gb, acc0=ga is not None, acc1=gb is not None)
+        grads[id(blk.norm0.weight)] = dg
+        grads[id(blk.norm0.bias)] = db
+        gbuf[id(xa)] = dxa
+        if xb is not None:
+            gbuf[id(xb)] = dxb
+
+
+def _unet_param_list(unet):
+    return [p for p in unet.parameters()]
+
+
+def _collect_grads(params, grads, zero_cache):
+    """Gradient tuple for autograd.Function.backward: live grads, zeros for affine.weight (the reference gives
+    them an all-zero gradient because emb == 0), None for the never-used map_layer*."""
+    out = []
+    for name, p in params:
+        g = grads.get(id(p))
+        if g is None and name.endswith('affine.weight'):
+            z = zero_cache.get(id(p))
+            if z is None or z.shape != p.shape or z.device != p.device:
+                z = torch.zeros_like(p)
+                zero_cache[id(p)] = z
+            g = z
+        out.append(g)
+    return out
+
+
+class _UNetFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, unet, x, *params):
+        eng = unet.engine()
+        ctx.unet = unet
+        xs = ops.nchw_to_nhwc(x.contiguous(), eng.dtype)
+        eng._step += 1
+        feat, tape = eng.forward(xs, unet.training, True, seed_base=_seed_base(eng._step))
+        ctx.tape = tape
+        return ops.nhwc_to_nchw(feat)
+
+    @staticmethod
+    def backward(ctx, dout):
+        unet = ctx.unet
+        eng = unet.engine()
+        dfeat = ops.nchw_to_nhwc(dout.contiguous().float(), eng.dtype)
+        grads = eng.backward(ctx.tape, dfeat, {})
+        ctx.tape = None
+        named = list(unet.named_parameters())
+        if not hasattr(unet, '_zero_cache'):
+            unet._zero_cache = {}
+        return (None, None) + tuple(_collect_grads(named, grads, unet._zero_cache))
+
+
+def _seed_base(step):
+    # per-process stream: torch's seed, the rank and the step counter; 64 blocks per step at most
+    rank = int(os.environ.get('RANK', '0'))
+    return (torch.initial_seed() * 1000003 + rank * 7919 + step) * 64 % (1 << 62)
+
+
+def unet_apply(unet, x):
+    _require_cuda(x, 'input')
+    params = [p for _, p in unet.named_parameters()]
+    if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+        return _UNetFunction.apply(unet, x, *params)
+    eng = unet.engine()
+    xs = ops.nchw_to_nhwc(x.contiguous(), eng.dtype)
+    eng._step += 1
+    feat, _ = eng.forward(xs, unet.training, False, seed_base=_seed_base(eng._step))
+    return ops.nhwc_to_nchw(feat)
+
+
+# ======================================================================================================================
+# prior / posterior encoders (prob_unet.py:8-78)
+# ======================================================================================================================
+class GaussianEngine:
+    def __init__(self, net, dtype):
+        self.net = net
+        self.dtype = dtype
+        self.cache = _PackCache()
+
+    def w_fwd(self, p):
+        return self.cache.get((id(p), 'f', self.dtype), p, lambda: ops.pack_weight(p.detach(), 0, self.dtype))
+
+    def w_dgrad(self, p):
+        return self.cache.get((id(p), 'd', self.dtype), p, lambda: ops.pack_weight(p.detach(), 1, self.dtype))
+
+    def convs(self):
+        return [m for m in self.net.encoder if isinstance(m, torch.nn.Conv2d)]
+
+    def forward(self, xin, save):
+        """xin: NHWC [N,H,W,Cin] (x, or x||target for the posterior).  Returns (mu, log_sigma, tape)."""
+        convs = self.convs()
+        x = xin
+        acts = []
+        for i, c in enumerate(convs):
+            r = ops.conv2d(x, self.w_fwd(c.weight), c.out_channels, 3, bias=c.bias, relu=True)
+            last = i == len(convs) - 1
+            acts.append((x, r))
+            if not last:
+                x = ops.avgpool2(r)
+        # AvgPool2d(2) followed by the global mean == global mean of r (H, W even)
+        if acts[-1][1].shape[1] % 2 or acts[-1][1].shape[2] % 2:
+            raise ValueError('prior/posterior encoder needs H, W divisible by 2**len(num_filters)')
+        m = ops.global_mean(acts[-1][1])
+        net = self.net
+        Lz = net.latent_dim
+        mu = ops.heads_fwd(m, net.conv_mu.weight, net.conv_mu.bias)
+        ls = ops.heads_fwd(m, net.conv_log_sigma.weight, net.conv_log_sigma.bias)
+        tape = dict(acts=acts, m=m) if save else None
+        return mu, ls, tape
+
+    def backward(self, tape, dmu, dls, grads):
+        net = self.net
+        convs = self.convs()
+        m = tape['m']
+        gw = torch.empty_like(net.conv_mu.weight)
+        gb = torch.empty_like(net.conv_mu.bias)
+        dm = ops.heads_bwd(m, net.conv_mu.weight, dmu, gw, gb)
+        grads[id(net.conv_mu.weight)] = gw
+        grads[id(net.conv_mu.bias)] = gb
+        gw = torch.empty_like(net.conv_log_sigma.weight)
+        gb = torch.empty_like(net.conv_log_sigma.bias)
+        ops.heads_bwd(m, net.conv_log_sigma.weight, dls, gw, gb, dm=dm)
+        grads[id(net.conv_log_sigma.weight)] = gw
+        grads[id(net.conv_log_sigma.bias)] = gb
+        dp = None
+        for i in reversed(range(len(convs))):
+            c = convs[i]
+            x, r = tape['acts'][i]
+            if i == len(convs) - 1:
+                dr = ops.relu_mean_bwd(dm, r)
+            else:
+                dr = ops.relu_pool_bwd(dp, r)
+            dwp = ops.conv2d_wgrad(x, dr, 3)
+            g = torch.empty_like(c.weight)
+            ops.unpack_wgrad(dwp, g)
+            grads[id(c.weight)] = g
+            grads[id(c.bias)] = ops.bias_grad(dr)
+            if i > 0:
+                dp = ops.conv2d(dr, self.w_dgrad(c.weight), c.in_channels, 3)
+        return grads
