@@ -97,7 +97,12 @@ _lib = None
 
 
 def lib():
-    """Loads the shared library (building it first if the sources are newer and nvcc is available)."""
+    """The loaded C ABI (or its event-recording proxy while profiling is active)."""
+    return _profiled if _profiled is not None else _raw_lib()
+
+
+def _raw_lib():
+    """Loads the shared library (building it first if it is missing and nvcc is available)."""
     global _lib
     if _lib is not None:
         return _lib
@@ -122,9 +127,86 @@ def exported_symbols():
     return sorted(_SIGNATURES)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# optional per-call timing (CUDA events on the launching stream) -- used by bench.py for the roofline numbers
+# ---------------------------------------------------------------------------------------------------------------------
+class CallProfiler:
+    """While active, every pu_* call is bracketed by two CUDA events on the current stream.  For the convolution
+    entry points the algorithmic FLOPs (2*M*N*K of the implicit GEMM) are recorded from the argument struct."""
+
+    def __init__(self):
+        self.records = []   # (name, kind, flops, start_event, end_event)
+
+    @staticmethod
+    def _conv_info(name, args):
+        if name not in ('pu_conv2d', 'pu_conv2d_wgrad'):
+            return name, 0.0
+        a = args[0]._obj
+        ctot = a.C0 + a.C1
+        flops = 2.0 * a.N * a.H * a.W * a.Cout * a.ksize * a.ksize * ctot
+        tc = (a.dtype == PU_BF16 and a.C0 % 64 == 0 and a.C1 % 64 == 0 and a.Cout % 64 == 0 and a.W >= 16
+              and a.H >= (8 if name == 'pu_conv2d' else 4) and not (a.flags & CONV_FORCE_SIMPLE))
+        kind = ('conv_tc' if name == 'pu_conv2d' else 'wgrad_tc') if tc else \
+               ('conv_simple' if name == 'pu_conv2d' else 'wgrad_simple')
+        return kind, flops
+
+    def wrap(self, name, fn):
+        def call(*args):
+            kind, flops = self._conv_info(name, args)
+            s = torch.cuda.Event(enable_timing=True)
+            e = torch.cuda.Event(enable_timing=True)
+            s.record()
+            rc = fn(*args)
+            e.record()
+            self.records.append((name, kind, flops, s, e))
+            return rc
+        return call
+
+    def summary(self):
+        """{kind: dict(calls, ms, flops)} -- call after torch.cuda.synchronize()."""
+        out = {}
+        for name, kind, flops, s, e in self.records:
+            d = out.setdefault(kind, dict(calls=0, ms=0.0, flops=0.0))
+            d['calls'] += 1
+            d['ms'] += s.elapsed_time(e)
+            d['flops'] += flops
+        return out
+
+
+class _ProfiledLib:
+    def __init__(self, handle, prof):
+        self._h = handle
+        self._p = prof
+        self._cache = {}
+
+    def __getattr__(self, name):
+        fn = self._cache.get(name)
+        if fn is None:
+            raw = getattr(self._h, name)
+            fn = self._p.wrap(name, raw) if name in _SIGNATURES and name not in (
+                'pu_last_error', 'pu_version', 'pu_launch_count', 'pu_device_supports_tc') else raw
+            self._cache[name] = fn
+        return fn
+
+
+_profiled = None
+
+
+def start_profiling():
+    global _profiled
+    prof = CallProfiler()
+    _profiled = _ProfiledLib(_raw_lib(), prof)
+    return prof
+
+
+def stop_profiling():
+    global _profiled
+    _profiled = None
+
+
 def check(rc, what=''):
     if rc != 0:
-        msg = lib().pu_last_error().decode(errors='replace')
+        msg = _raw_lib().pu_last_error().decode(errors='replace')
         if rc == -1:
             raise ValueError(f'probunet_b200 {what}: {msg}')
         raise RuntimeError(f'probunet_b200 {what} failed (rc={rc}): {msg}')
