@@ -49,12 +49,12 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index = index
         self.rows = []
-        self._stop = threading.Event()
+        self._halt = threading.Event()
 
     def run(self):
         q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(['nvidia-smi', f'--query-gpu={q}', '--format=csv,noheader,nounits', '-i',
                                       str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
@@ -62,10 +62,10 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(',')])
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=5)
         sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
         reasons = set()

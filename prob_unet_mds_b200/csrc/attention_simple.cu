@@ -351,7 +351,7 @@ int pu_attention_bwd(const void* qkv, const void* out, const void* dout, const f
     cudaStream_t st = (cudaStream_t)stream;
     int rc = pu::attention_delta(out, dout, delta_ws, N, T, heads, dtype, st);
     if (rc) return rc;
-    if (!(flags & PU_CONV_FORCE_SIMPLE) && pu::attention_tc_applicable(N, T, heads, dtype))
+    if (!(flags & PU_CONV_FORCE_SIMPLE) && pu::attention_bwd_tc_applicable(N, T, heads, dtype))
         return pu::attention_bwd_tc(qkv, dout, lse, delta_ws, dqkv, N, T, heads, st);
     PU_REQUIRE(!(flags & PU_CONV_FORCE_TC), "pu_attention_bwd: tcgen05 kernel does not apply (T=%d dtype=%d)", T, dtype);
     return pu::attention_bwd_simple(qkv, dout, lse, delta_ws, dqkv, N, T, heads, dtype, st);

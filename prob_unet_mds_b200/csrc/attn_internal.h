@@ -8,6 +8,7 @@ int attention_delta(const void* out, const void* dout, float* delta, int N, int 
 int attention_bwd_simple(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, int N,
                          int T, int heads, int dtype, cudaStream_t st);
 bool attention_tc_applicable(int N, int T, int heads, int dtype);
+bool attention_bwd_tc_applicable(int N, int T, int heads, int dtype);
 int attention_fwd_tc(const void* qkv, void* out, float* lse, int N, int T, int heads, cudaStream_t st);
 int attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv, int N, int T,
                      int heads, cudaStream_t st);

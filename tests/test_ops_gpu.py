@@ -304,6 +304,27 @@ def test_attention_simple(N, T, heads, dtype):
     assert rel_err(dqkv, qkv.grad) < (1e-4 if dtype == 'f32' else 1.5e-2)
 
 
+@pytest.mark.parametrize('N,T,heads', [(2, 128, 2), (1, 256, 4), (2, 1024, 4), (1, 4096, 4), (3, 384, 6)])
+def test_attention_tc(N, T, heads):
+    dt = torch.bfloat16
+    Cc = heads * 64
+    qkv = (rnd(N, T, 3 * Cc, seed=1) * 1.5).to(dt).float().requires_grad_(True)
+    ref = _attn_ref(qkv, heads)
+    dout = rnd(N, T, Cc, seed=2).to(dt).float()
+    ref.backward(dout)
+    out, lse = ops.attention_fwd(qkv.detach().to(dt), heads, flags=L.CONV_FORCE_TC)
+    q, k, _ = [t.reshape(N, T, heads, 64).permute(0, 2, 1, 3) for t in qkv.detach().split(Cc, dim=-1)]
+    lse_ref = torch.logsumexp(q @ k.transpose(-1, -2) / 8.0, dim=-1)
+    e = rel_err(out, ref)
+    print(f'attention_tc fwd N={N} T={T} heads={heads}: rel {e:.3e}, lse max err {max_err(lse, lse_ref):.3e}')
+    assert e < 6e-3
+    assert max_err(lse, lse_ref) < 2e-3
+    dqkv = ops.attention_bwd(qkv.detach().to(dt), out, dout.to(dt), lse, heads)
+    eb = rel_err(dqkv, qkv.grad)
+    print(f'attention bwd N={N} T={T} heads={heads}: rel {eb:.3e}')
+    assert eb < 1.5e-2
+
+
 def test_encoder_glue():
     x = rnd(2, 64, 8, 8, seed=1)
     xs = nhwc(x, torch.float32)
