@@ -142,8 +142,10 @@ int pu_gn_bwd(const PuGnBwdArgs* a, void* stream);
  * out [N][T][C] with channel order (head, d).  lse [N][heads][T] fp32 = log-sum-exp of the scaled logits.  */
 int pu_attention_fwd(const void* qkv, void* out, float* lse, int N, int T, int heads, int dtype, int flags,
                      void* stream);
+/* workspaces: delta_ws fp32 [N][heads][T] (sum_d out*dout); dq_ws fp32 [N][T][C] (cross-key-tile reduction of dq,
+ * only touched by the tcgen05 kernel)                                                                          */
 int pu_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
-                     float* delta_ws, int N, int T, int heads, int dtype, int flags, void* stream);
+                     float* delta_ws, float* dq_ws, int N, int T, int heads, int dtype, int flags, void* stream);
 
 /* ---------------- prior / posterior encoders (prob_unet.py:32-36,60-72) ---------------- */
 /* y[N,2H,2W,C] = nearest-neighbour x2 of x (skip branch of the "up" blocks, networks.py:82-83,156) */

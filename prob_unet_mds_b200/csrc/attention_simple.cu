@@ -344,15 +344,15 @@ int pu_attention_fwd(const void* qkv, void* out, float* lse, int N, int T, int h
 }
 
 int pu_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
-                     float* delta_ws, int N, int T, int heads, int dtype, int flags, void* stream) {
-    PU_REQUIRE(qkv && out && dout && lse && dqkv && delta_ws && N > 0 && T > 0 && heads > 0,
+                     float* delta_ws, float* dq_ws, int N, int T, int heads, int dtype, int flags, void* stream) {
+    PU_REQUIRE(qkv && out && dout && lse && dqkv && delta_ws && dq_ws && N > 0 && T > 0 && heads > 0,
                "pu_attention_bwd: bad arguments");
     PU_REQUIRE(dtype == PU_F32 || dtype == PU_BF16, "pu_attention_bwd: bad dtype");
     cudaStream_t st = (cudaStream_t)stream;
     int rc = pu::attention_delta(out, dout, delta_ws, N, T, heads, dtype, st);
     if (rc) return rc;
     if (!(flags & PU_CONV_FORCE_SIMPLE) && pu::attention_bwd_tc_applicable(N, T, heads, dtype))
-        return pu::attention_bwd_tc(qkv, dout, lse, delta_ws, dqkv, N, T, heads, st);
+        return pu::attention_bwd_tc(qkv, dout, lse, delta_ws, dqkv, dq_ws, N, T, heads, st);
     PU_REQUIRE(!(flags & PU_CONV_FORCE_TC), "pu_attention_bwd: tcgen05 kernel does not apply (T=%d dtype=%d)", T, dtype);
     return pu::attention_bwd_simple(qkv, dout, lse, delta_ws, dqkv, N, T, heads, dtype, st);
 }

@@ -284,11 +284,300 @@ int attention_fwd_tc(const void* qkv, void* out, float* lse, int N, int T, int h
     return check_launch("attn_fwd_tc");
 }
 
-bool attention_bwd_tc_applicable(int, int, int, int) { return false; }
+// ------------------------------------------------------------------------------------------------
+// backward: one CTA per (key tile of 128, sample*head), walking the query tiles.
+//   S  = Q_i K_j^T, dP = dO_i V_j^T                      (K-major operands)            -> TMEM
+//   P  = exp2(S*sc - lse_i), dS = P (dP - delta_i) / 8   (softmax warps)               -> shared (SW128, [q][k])
+//   dV += P^T dO_i, dK += dS^T Q_i                       (P/dS and dO/Q as MN-major operands, accumulate in TMEM)
+//   dQ_i = dS K_j                                        (dS K-major, K_j MN-major)    -> TMEM -> red.add.v4 (fp32)
+// dQ partial sums of the different key tiles are combined with vectorised fp32 reductions into dq_acc [N*T][C].
+// ------------------------------------------------------------------------------------------------
+constexpr int AB_QD_STAGES = 2;
+constexpr int AB_SMEM = 2 * AT_TILE /*K,V*/ + AB_QD_STAGES * 2 * AT_TILE /*Q,dO*/ + 2 * AT_TILE /*P*/ + 2 * AT_TILE /*dS*/ +
+                        1024 + 256;
 
-int attention_bwd_tc(const void*, const void*, const float*, const float*, void*, int, int, int, cudaStream_t) {
-    set_error("attention_bwd_tc: not built");
-    return PU_ERR_UNSUPPORTED;
+struct AttnBwdParams {
+    int T, heads, C;
+    const float* lse;
+    const float* delta;
+    float* dq_acc;            // [N*T][C] fp32, zeroed by the caller
+    __nv_bfloat16* dqkv;      // [N*T][3C]
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                   const AttnBwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sK = smem;
+    uint8_t* sV = sK + AT_TILE;
+    uint8_t* sQD = sV + AT_TILE;                           // stage s: Q at +s*2*TILE, dO at +s*2*TILE + TILE
+    uint8_t* sP = sQD + AB_QD_STAGES * 2 * AT_TILE;        // two 64-key blocks of [128 q][128 B]
+    uint8_t* sDS = sP + 2 * AT_TILE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + 2 * AT_TILE);
+    uint64_t* kv_full = bars;
+    uint64_t* qd_full = bars + 1;                          // [2]
+    uint64_t* qd_empty = qd_full + AB_QD_STAGES;
+    uint64_t* sdp_full = qd_empty + AB_QD_STAGES;
+    uint64_t* pds_full = sdp_full + 1;
+    uint64_t* dq_full = pds_full + 1;
+    uint64_t* dq_empty = dq_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_empty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nh = blockIdx.y, n = nh / p.heads, h = nh % p.heads;
+    const int k0 = blockIdx.x * AT_TK;
+    const int nq = p.T / AT_TQ;
+    const int row_base = n * p.T;
+    const int colQ = h * AT_D, colK = p.C + h * AT_D, colV = 2 * p.C + h * AT_D;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmQKV);
+        prefetch_tmap(&tmDO);
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(smem_u32(kv_full), 1);
+        for (int s = 0; s < AB_QD_STAGES; ++s) {
+            mbar_init(smem_u32(&qd_full[s]), 1);
+            mbar_init(smem_u32(&qd_empty[s]), 1);
+        }
+        mbar_init(smem_u32(sdp_full), 1);
+        mbar_init(smem_u32(pds_full), 4);
+        mbar_init(smem_u32(dq_full), 1);
+        mbar_init(smem_u32(dq_empty), 4);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(smem_u32(tmem_slot), 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320,
+                   tDQ = tmem_base + 384;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(smem_u32(kv_full), 2 * AT_TILE);
+            tma_load_2d(smem_u32(sK), &tmQKV, smem_u32(kv_full), colK, row_base + k0);
+            tma_load_2d(smem_u32(sV), &tmQKV, smem_u32(kv_full), colV, row_base + k0);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int i = 0; i < nq; ++i) {
+                mbar_wait(smem_u32(&qd_empty[stage]), phase ^ 1);
+                const uint32_t fb = smem_u32(&qd_full[stage]);
+                mbar_expect_tx(fb, 2 * AT_TILE);
+                tma_load_2d(smem_u32(sQD + stage * 2 * AT_TILE), &tmQKV, fb, colQ, row_base + i * AT_TQ);
+                tma_load_2d(smem_u32(sQD + stage * 2 * AT_TILE + AT_TILE), &tmDO, fb, colQ, row_base + i * AT_TQ);
+                if (++stage == AB_QD_STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t IDESC_S = idesc_bf16_f32(128, 128, 0, 0);     // S, dP
+            constexpr uint32_t IDESC_T = idesc_bf16_f32(128, 64, 1, 1);      // dV, dK (both operands MN-major)
+            constexpr uint32_t IDESC_Q = idesc_bf16_f32(128, 64, 0, 1);      // dQ
+            const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+            const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
+            mbar_wait(smem_u32(kv_full), 0);
+            auto issue_sdp = [&](int stage) {
+                const uint32_t q_addr = smem_u32(sQD + stage * 2 * AT_TILE);
+                const uint32_t do_addr = q_addr + AT_TILE;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    mma_f16_ss(tS, smem_desc_sw128(q_addr + k * 32, 16, 1024), smem_desc_sw128(k_addr + k * 32, 16, 1024),
+                               IDESC_S, k ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    mma_f16_ss(tDP, smem_desc_sw128(do_addr + k * 32, 16, 1024),
+                               smem_desc_sw128(v_addr + k * 32, 16, 1024), IDESC_S, k ? 1u : 0u);
+                mma_commit(smem_u32(sdp_full));
+            };
+            int stage = 0;
+            uint32_t phase = 0;
+            mbar_wait(smem_u32(&qd_full[0]), 0);
+            tc_fence_after();
+            issue_sdp(0);
+            for (int i = 0; i < nq; ++i) {
+                mbar_wait(smem_u32(pds_full), i & 1);
+                mbar_wait(smem_u32(dq_empty), (i & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t q_addr = smem_u32(sQD + stage * 2 * AT_TILE);
+                const uint32_t do_addr = q_addr + AT_TILE;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {   // K = 128 query rows, 16 per step
+                    mma_f16_ss(tDV, smem_desc_sw128(p_addr + k * 2048, AT_TILE, 1024),
+                               smem_desc_sw128(do_addr + k * 2048, AT_TILE, 1024), IDESC_T, (i | k) ? 1u : 0u);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    mma_f16_ss(tDK, smem_desc_sw128(ds_addr + k * 2048, AT_TILE, 1024),
+                               smem_desc_sw128(q_addr + k * 2048, AT_TILE, 1024), IDESC_T, (i | k) ? 1u : 0u);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {   // K = 128 keys: two 64-key blocks x four 16-key steps
+                    mma_f16_ss(tDQ, smem_desc_sw128(ds_addr + (k >> 2) * AT_TILE + (k & 3) * 32, 16, 1024),
+                               smem_desc_sw128(k_addr + k * 2048, AT_TILE, 1024), IDESC_Q, k ? 1u : 0u);
+                }
+                mma_commit(smem_u32(dq_full));
+                mma_commit(smem_u32(&qd_empty[stage]));
+                if (++stage == AB_QD_STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+                if (i + 1 < nq) {
+                    mbar_wait(smem_u32(&qd_full[stage]), phase);
+                    tc_fence_after();
+                    issue_sdp(stage);
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp - 4;
+        const int r = q * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        const float sc = 0.125f * 1.4426950408889634f;
+        const float* lse = p.lse + ((long long)n * p.heads + h) * p.T;
+        const float* delta = p.delta + ((long long)n * p.heads + h) * p.T;
+        for (int i = 0; i < nq; ++i) {
+            const float l2 = lse[i * AT_TQ + r] * 1.4426950408889634f;
+            const float dl = delta[i * AT_TQ + r];
+            mbar_wait(smem_u32(sdp_full), i & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < AT_TK; c += 32) {
+                uint32_t sv[32], dv[32];
+                tmem_ld32(tS + lane_off + c, sv);
+                tmem_ld32(tDP + lane_off + c, dv);
+                tc_wait_ld();
+                uint8_t* pb = sP + (c >> 6) * AT_TILE + r * 128;
+                uint8_t* db = sDS + (c >> 6) * AT_TILE + r * 128;
+                const int chunk0 = (c & 63) >> 3;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint4 pk, dk;
+                    __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&pk);
+                    __nv_bfloat162* hd = reinterpret_cast<__nv_bfloat162*>(&dk);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int i0 = g * 8 + 2 * e;
+                        const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i0]), sc, -l2));
+                        const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i0 + 1]), sc, -l2));
+                        const float d0 = p0 * (__uint_as_float(dv[i0]) - dl) * 0.125f;
+                        const float d1 = p1 * (__uint_as_float(dv[i0 + 1]) - dl) * 0.125f;
+                        hp[e] = __floats2bfloat162_rn(p0, p1);
+                        hd[e] = __floats2bfloat162_rn(d0, d1);
+                    }
+                    const int off = ((chunk0 + g) ^ (r & 7)) << 4;
+                    *reinterpret_cast<uint4*>(pb + off) = pk;
+                    *reinterpret_cast<uint4*>(db + off) = dk;
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(pds_full));
+            // dQ_i partial -> fp32 reduction
+            mbar_wait(smem_u32(dq_full), i & 1);
+            tc_fence_after();
+            float* dst = p.dq_acc + ((long long)row_base + i * AT_TQ + r) * p.C + h * AT_D;
+#pragma unroll
+            for (int c = 0; c < AT_D; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(tDQ + lane_off + c, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 32; e += 4)
+                    red_add_v4(dst + c + e, __uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]),
+                               __uint_as_float(v[e + 3]));
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(dq_empty));
+        }
+        // the last dq_full commit also covers the final dV / dK accumulation
+        __nv_bfloat16* kp = p.dqkv + ((long long)row_base + k0 + r) * 3 * p.C + colK;
+        __nv_bfloat16* vp = p.dqkv + ((long long)row_base + k0 + r) * 3 * p.C + colV;
+#pragma unroll
+        for (int c = 0; c < AT_D; c += 32) {
+            uint32_t a[32], b[32];
+            tmem_ld32(tDK + lane_off + c, a);
+            tmem_ld32(tDV + lane_off + c, b);
+            tc_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 32; e += 8) {
+                float ka[8], va[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    ka[u] = __uint_as_float(a[e + u]);
+                    va[u] = __uint_as_float(b[e + u]);
+                }
+                st8(kp + c + e, ka);
+                st8(vp + c + e, va);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// dqkv[row][0:C] = bf16(dq_acc[row][:])
+__global__ void attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, long long rows,
+                                       int C) {
+    const int nvec = C / 8;
+    const long long total = rows * nvec;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i % nvec);
+        const long long row = i / nvec;
+        float x[8];
+        ld8(acc + row * C + v * 8, x);
+        st8(dqkv + row * 3 * C + v * 8, x);
+    }
+}
+
+bool attention_bwd_tc_applicable(int N, int T, int heads, int dtype) { return attention_tc_applicable(N, T, heads, dtype); }
+
+int attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv,
+                     float* dq_acc, int N, int T, int heads, cudaStream_t st) {
+    const int C = heads * AT_D;
+    CUtensorMap tm, tmdo;
+    int rc = make_mat_tmap(&tm, qkv, (long long)N * T, 3LL * C, 128);
+    if (rc) return rc;
+    rc = make_mat_tmap(&tmdo, dout, (long long)N * T, (long long)C, 128);
+    if (rc) return rc;
+    static bool attr = false;
+    if (!attr) {
+        PU_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+        attr = true;
+    }
+    PU_CUDA(cudaMemsetAsync(dq_acc, 0, sizeof(float) * (size_t)N * T * C, st));
+    AttnBwdParams p;
+    p.T = T; p.heads = heads; p.C = C;
+    p.lse = lse; p.delta = delta; p.dq_acc = dq_acc;
+    p.dqkv = (__nv_bfloat16*)dqkv;
+    dim3 grid(T / AT_TK, N * heads);
+    attn_bwd_tc_kernel<<<grid, 256, AB_SMEM, st>>>(tm, tmdo, p);
+    rc = check_launch("attn_bwd_tc");
+    if (rc) return rc;
+    long long total = (long long)N * T * (C / 8);
+    long long g = cdivll(total, 256);
+    if (g > 148 * 16) g = 148 * 16;
+    attn_dq_convert_kernel<<<(unsigned)g, 256, 0, st>>>(dq_acc, (__nv_bfloat16*)dqkv, (long long)N * T, C);
+    return check_launch("attn_dq_convert");
 }
 
 }  // namespace pu

@@ -180,8 +180,9 @@ def attention_bwd(qkv, out, dout, lse, heads, flags=0):
     T = qkv.numel() // (N * C3)
     dqkv = torch.empty_like(qkv)
     delta = torch.empty((N, heads, T), dtype=torch.float32, device=qkv.device)
-    check(lib().pu_attention_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(dqkv), ptr(delta), N, T, heads,
-                                 dtype_code(qkv.dtype), flags, stream_ptr()), 'attention_bwd')
+    dq_ws = torch.empty((N, T, C3 // 3), dtype=torch.float32, device=qkv.device)
+    check(lib().pu_attention_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(dqkv), ptr(delta), ptr(dq_ws), N, T,
+                                 heads, dtype_code(qkv.dtype), flags, stream_ptr()), 'attention_bwd')
     return dqkv
 
 
