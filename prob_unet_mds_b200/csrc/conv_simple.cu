@@ -211,6 +211,36 @@ __global__ void bias_grad_kernel(const T* __restrict__ dy, float* __restrict__ d
     }
 }
 
+// vectorised variant: thread (v, pl) sums channels [8v, 8v+8) over pixels pl, pl+PL, ... of the block's range
+template <typename T>
+__global__ void __launch_bounds__(256) bias_grad_vec_kernel(const T* __restrict__ dy, float* __restrict__ db, long long P,
+                                                            int C, int rows) {
+    extern __shared__ float sm[];   // [C]
+    const int nvec = C / 8;
+    const int PL = 256 / nvec;
+    const int v = threadIdx.x % nvec, pl = threadIdx.x / nvec;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    long long p0 = (long long)blockIdx.x * rows;
+    long long p1 = p0 + rows;
+    if (p1 > P) p1 = P;
+    if (pl < PL) {
+        float s[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s[e] = 0.f;
+        for (long long p = p0 + pl; p < p1; p += PL) {
+            float x[8];
+            ld8(dy + p * C + v * 8, x);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s[e] += x[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(&sm[v * 8 + e], s[e]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(db + i, sm[i]);
+}
+
 int conv_simple_launch(const PuConvArgs* a, cudaStream_t st) {
     long long M = (long long)a->N * a->H * a->W;
     dim3 grid((unsigned)cdivll(M, TS), (unsigned)cdiv(a->Cout, TS));
@@ -247,6 +277,18 @@ extern "C" int pu_bias_grad(const void* dy, float* db, long long pixels, int C, 
     cudaStream_t st = (cudaStream_t)stream;
     PU_REQUIRE(dy && db && pixels > 0 && C > 0, "pu_bias_grad: bad arguments");
     if (!accumulate) PU_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * C, st));
+    if (C % 8 == 0 && C / 8 <= 256) {
+        const int PL = 256 / (C / 8);
+        int rows = (int)pu::cdivll(pixels, 148 * 8);
+        if (rows < PL * 8) rows = PL * 8;
+        unsigned grid = (unsigned)pu::cdivll(pixels, rows);
+        if (dtype == PU_F32)
+            pu::bias_grad_vec_kernel<float><<<grid, 256, sizeof(float) * C, st>>>((const float*)dy, db, pixels, C, rows);
+        else
+            pu::bias_grad_vec_kernel<__nv_bfloat16><<<grid, 256, sizeof(float) * C, st>>>((const __nv_bfloat16*)dy, db,
+                                                                                         pixels, C, rows);
+        return pu::check_launch("bias_grad_vec");
+    }
     int rows = (int)pu::cdivll(pixels, 148 * 8);
     if (rows < 32) rows = 32;
     unsigned grid = (unsigned)pu::cdivll(pixels, rows);

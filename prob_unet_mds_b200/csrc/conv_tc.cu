@@ -503,9 +503,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
                 tc_wait_ld();
                 if (has_work && co < p.Cout) {
                     float* dst = p.dw + co * row_stride + (long long)tap * Ctot + ci_t * BN + c;
+                    // BN divides C0+C1 (host picks BN that way), so the whole 32-column chunk is in range
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (ci_t * BN + c + j < Ctot) atomicAdd(dst + j, __uint_as_float(v[j]));
+                    for (int j = 0; j < 32; j += 4) {
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j),
+                                     "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])),
+                                     "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                                     : "memory");
                     }
                 }
             }

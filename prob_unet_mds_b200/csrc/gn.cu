@@ -1,6 +1,12 @@
 // GroupNorm (+adaptive scale/shift, SiLU, dropout, 2x resample) forward and backward, NHWC, HBM-bound.
 // Replaces F.group_norm / silu / addcmul / dropout and the depthwise resample convs around them
 // (networks.py:104,166,170-171,175,82-85).  Statistics are accumulated in fp64.
+//
+// Thread mapping (all kernels): a block is a (channel-vector, pixel-lane) grid of 256 threads.  Thread (v, pl) owns the
+// 8 channels [8v, 8v+8) -- its per-channel constants (mean, rstd, gamma', beta') live in registers -- and walks the
+// pixels pl, pl+PL, ... of the block's pixel range, so a warp reads/writes contiguous 16-byte vectors and no integer
+// division is needed per element.  Algorithmic traffic per element: apply 2B read + 2B write (bf16); backward
+// 4B read (reduce pass) + 4..6B read + 2B write (apply pass).
 #include "../../include/probunet_b200.h"
 #include "common.cuh"
 
@@ -8,46 +14,47 @@ namespace pu {
 
 constexpr int GN_THREADS = 256;
 
-// ---- helpers shared by forward and backward ----
-struct GnSmem {
-    float* mu;    // [C] group mean per channel
-    float* rstd;  // [C]
-    float* gam;   // [C] gamma' = gamma * (1 + scale)
-    float* bet;   // [C] beta'  = beta * (1 + scale) + shift
-};
-
-__device__ __forceinline__ GnSmem gn_smem(float* base, int C) {
-    GnSmem s;
-    s.mu = base;
-    s.rstd = base + C;
-    s.gam = base + 2 * C;
-    s.bet = base + 3 * C;
-    return s;
+template <bool FAST>
+__device__ __forceinline__ float sigmoid_t(float u) {
+    return FAST ? __fdividef(1.f, 1.f + __expf(-u)) : 1.f / (1.f + expf(-u));
 }
 
-__device__ __forceinline__ void gn_setup(const PuGnArgs& f, int n, const GnSmem& s) {
+struct ChanConst {
+    float mu[8], rstd[8], gam[8], bet[8];
+};
+
+// per-thread constants of channels [c0, c0+8) of sample n
+__device__ __forceinline__ void gn_load_consts(const PuGnArgs& f, int n, int c0, ChanConst& k) {
     const int C = f.C0 + f.C1;
     const int Cg = C / f.G;
     const double m = (double)Cg * f.H * f.W;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    int gprev = -1;
+    float mean = 0.f, rstd = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int c = c0 + e;
         const int g = c / Cg;
-        const double sum = f.stats[((long long)n * f.G + g) * 2];
-        const double ssq = f.stats[((long long)n * f.G + g) * 2 + 1];
-        const double mean = sum / m;
-        double var = ssq / m - mean * mean;
-        if (var < 0) var = 0;
+        if (g != gprev) {
+            const double sum = f.stats[((long long)n * f.G + g) * 2];
+            const double ssq = f.stats[((long long)n * f.G + g) * 2 + 1];
+            const double mm = sum / m;
+            double var = ssq / m - mm * mm;
+            if (var < 0) var = 0;
+            mean = (float)mm;
+            rstd = (float)(1.0 / sqrt(var + (double)f.eps));
+            gprev = g;
+        }
         float gam = f.gamma[c], bet = f.beta[c];
         if (f.ada) {
             const float sc = f.ada[c], sh = f.ada[C + c];
             gam = gam * (1.f + sc);
             bet = fmaf(bet, 1.f + sc, sh);
         }
-        s.mu[c] = (float)mean;
-        s.rstd[c] = (float)(1.0 / sqrt(var + (double)f.eps));
-        s.gam[c] = gam;
-        s.bet[c] = bet;
+        k.mu[e] = mean;
+        k.rstd[e] = rstd;
+        k.gam[e] = gam;
+        k.bet[e] = bet;
     }
-    __syncthreads();
 }
 
 template <typename T>
@@ -78,86 +85,101 @@ gn_stats_kernel(const T* __restrict__ s0, const T* __restrict__ s1, int C0, int 
 #pragma unroll
         for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
         const int c0 = v * 8;
+        const T* base = (c0 < C0) ? (s0 + (long long)n * HW * C0 + c0) : (s1 + (long long)n * HW * C1 + (c0 - C0));
+        const int stride = (c0 < C0) ? C0 : C1;
         for (int r = r0 + pl; r < r1; r += PL) {
-            const long long pix = (long long)n * HW + r;
             float x[8];
-            if (c0 < C0)
-                ld8(s0 + pix * C0 + c0, x);
-            else
-                ld8(s1 + pix * C1 + (c0 - C0), x);
+            ld8(base + (long long)r * stride, x);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 s[e] += x[e];
                 q[e] = fmaf(x[e], x[e], q[e]);
             }
         }
+        // combine channels of the same group before touching shared memory
+        int g = c0 / Cg;
+        float gs = 0.f, gq = 0.f;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const int g = (c0 + e) / Cg;
-            atomicAdd(&sm[2 * g], s[e]);
-            atomicAdd(&sm[2 * g + 1], q[e]);
+            const int ge = (c0 + e) / Cg;
+            if (ge != g) {
+                atomicAdd(&sm[2 * g], gs);
+                atomicAdd(&sm[2 * g + 1], gq);
+                g = ge;
+                gs = gq = 0.f;
+            }
+            gs += s[e];
+            gq += q[e];
         }
+        atomicAdd(&sm[2 * g], gs);
+        atomicAdd(&sm[2 * g + 1], gq);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(stats + (long long)n * G * 2 + i, (double)sm[i]);
 }
 
 // ---- forward apply ----
-template <typename T>
+template <typename T, bool FAST>
 __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(PuGnArgs f, int rows) {
-    extern __shared__ float sm[];
     const int C = f.C0 + f.C1, nvec = C / 8;
     const int n = blockIdx.y;
-    GnSmem s = gn_smem(sm, C);
-    gn_setup(f, n, s);
+    const int PL = GN_THREADS / nvec;
+    const int v = threadIdx.x % nvec, pl = threadIdx.x / nvec;
+    if (pl >= PL) return;
+    const int c0 = v * 8;
+    ChanConst k;
+    gn_load_consts(f, n, c0, k);
     const int OH = f.resample == PU_RS_UP ? f.H * 2 : (f.resample == PU_RS_DOWN ? f.H / 2 : f.H);
     const int OW = f.resample == PU_RS_UP ? f.W * 2 : (f.resample == PU_RS_DOWN ? f.W / 2 : f.W);
     const int r0 = blockIdx.x * rows;
     int r1 = r0 + rows;
     if (r1 > OH * OW) r1 = OH * OW;
     const float inv_keep = f.dropout_p > 0.f ? 1.f / (1.f - f.dropout_p) : 1.f;
-    T* y = reinterpret_cast<T*>(f.y);
-    const int total = (r1 - r0) * nvec;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int v = idx % nvec;
-        const int op = r0 + idx / nvec;
-        const int oy = op / OW, ox = op % OW;
-        const int c0 = v * 8;
+    T* y = reinterpret_cast<T*>(f.y) + (long long)n * OH * OW * C + c0;
+    const long long in_base = (long long)n * f.H * f.W;
+    for (int op = r0 + pl; op < r1; op += PL) {
         float o[8];
-        if (f.resample == PU_RS_DOWN) {
+        if (f.resample == PU_RS_NONE) {
+            float x[8];
+            gn_load_x8<T>(f, in_base + op, c0, x);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float u = fmaf((x[e] - k.mu[e]) * k.rstd[e], k.gam[e], k.bet[e]);
+                o[e] = f.silu ? u * sigmoid_t<FAST>(u) : u;
+            }
+        } else if (f.resample == PU_RS_UP) {
+            const int oy = op / OW, ox = op - oy * OW;
+            float x[8];
+            gn_load_x8<T>(f, in_base + (long long)(oy >> 1) * f.W + (ox >> 1), c0, x);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float u = fmaf((x[e] - k.mu[e]) * k.rstd[e], k.gam[e], k.bet[e]);
+                o[e] = f.silu ? u * sigmoid_t<FAST>(u) : u;
+            }
+        } else {
+            const int oy = op / OW, ox = op - oy * OW;
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] = 0.f;
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
-                const int iy = oy * 2 + (t >> 1), ix = ox * 2 + (t & 1);
                 float x[8];
-                gn_load_x8<T>(f, ((long long)n * f.H + iy) * f.W + ix, c0, x);
+                gn_load_x8<T>(f, in_base + (long long)(oy * 2 + (t >> 1)) * f.W + ox * 2 + (t & 1), c0, x);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    float u = fmaf((x[e] - s.mu[c0 + e]) * s.rstd[c0 + e], s.gam[c0 + e], s.bet[c0 + e]);
-                    o[e] += f.silu ? silu_f(u) : u;
+                    const float u = fmaf((x[e] - k.mu[e]) * k.rstd[e], k.gam[e], k.bet[e]);
+                    o[e] += f.silu ? u * sigmoid_t<FAST>(u) : u;
                 }
             }
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] *= 0.25f;
-        } else {
-            const int iy = f.resample == PU_RS_UP ? (oy >> 1) : oy;
-            const int ix = f.resample == PU_RS_UP ? (ox >> 1) : ox;
-            float x[8];
-            gn_load_x8<T>(f, ((long long)n * f.H + iy) * f.W + ix, c0, x);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                float u = fmaf((x[e] - s.mu[c0 + e]) * s.rstd[c0 + e], s.gam[c0 + e], s.bet[c0 + e]);
-                o[e] = f.silu ? silu_f(u) : u;
-            }
         }
-        const long long opix = (long long)n * OH * OW + op;
         if (f.dropout_p > 0.f) {
+            const long long opix = (long long)n * OH * OW + op;
             const uint32_t keep = dropout_keep8(f.seed, (unsigned long long)((opix * C + c0) >> 3), f.dropout_p);
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] = ((keep >> e) & 1u) ? o[e] * inv_keep : 0.f;
         }
-        st8(y + opix * C + c0, o);
+        st8(y + (long long)op * C, o);
     }
 }
 
@@ -165,11 +187,11 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(PuGnArgs f, int ro
 // gradient wrt the (pre-resample) activation output at input pixel (iy, ix): gathers dy through the transpose
 // of the forward resample
 template <typename T>
-__device__ __forceinline__ void gn_gather8(const T* dy, int rs, int n, int H, int W, int iy, int ix, int C, int c0,
-                                           float (&g)[8]) {
+__device__ __forceinline__ void gn_gather8(const T* dy, int rs, int n, int H, int W, int r, int C, int c0, float (&g)[8]) {
     if (rs == PU_RS_NONE) {
-        ld8(dy + (((long long)n * H + iy) * W + ix) * C + c0, g);
+        ld8(dy + ((long long)n * H * W + r) * C + c0, g);
     } else if (rs == PU_RS_UP) {
+        const int iy = r / W, ix = r - iy * W;
         const int OH = 2 * H, OW = 2 * W;
 #pragma unroll
         for (int e = 0; e < 8; ++e) g[e] = 0.f;
@@ -181,6 +203,7 @@ __device__ __forceinline__ void gn_gather8(const T* dy, int rs, int n, int H, in
             for (int e = 0; e < 8; ++e) g[e] += v[e];
         }
     } else {
+        const int iy = r / W, ix = r - iy * W;
         const int OH = H / 2, OW = W / 2;
         ld8(dy + (((long long)n * OH + (iy >> 1)) * OW + (ix >> 1)) * C + c0, g);
 #pragma unroll
@@ -189,14 +212,14 @@ __device__ __forceinline__ void gn_gather8(const T* dy, int rs, int n, int H, in
 }
 
 // du = d loss / d u  where u = xhat * gamma' + beta' and y = resample(dropout(act(u)))
-template <typename T>
-__device__ __forceinline__ void gn_du8(const PuGnArgs& f, const GnSmem& s, const T* dy, int n, int iy, int ix, int c0,
+template <typename T, bool FAST>
+__device__ __forceinline__ void gn_du8(const PuGnArgs& f, const ChanConst& k, const T* dy, int n, int r, int c0,
                                        float (&xh)[8], float (&du)[8]) {
     const int C = f.C0 + f.C1;
-    const long long pix = ((long long)n * f.H + iy) * f.W + ix;
+    const long long pix = (long long)n * f.H * f.W + r;
     float x[8], g[8];
     gn_load_x8<T>(f, pix, c0, x);
-    gn_gather8<T>(dy, f.resample, n, f.H, f.W, iy, ix, C, c0, g);
+    gn_gather8<T>(dy, f.resample, n, f.H, f.W, r, C, c0, g);
     uint32_t keep = 0xffu;
     float inv_keep = 1.f;
     if (f.dropout_p > 0.f) {
@@ -205,28 +228,27 @@ __device__ __forceinline__ void gn_du8(const PuGnArgs& f, const GnSmem& s, const
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        xh[e] = (x[e] - s.mu[c0 + e]) * s.rstd[c0 + e];
+        xh[e] = (x[e] - k.mu[e]) * k.rstd[e];
         float gg = ((keep >> e) & 1u) ? g[e] * inv_keep : 0.f;
         if (f.silu) {
-            float u = fmaf(xh[e], s.gam[c0 + e], s.bet[c0 + e]);
-            gg *= dsilu_f(u);
+            const float u = fmaf(xh[e], k.gam[e], k.bet[e]);
+            const float s = sigmoid_t<FAST>(u);
+            gg *= s * (1.f + u * (1.f - s));
         }
         du[e] = gg;
     }
 }
 
-template <typename T>
+template <typename T, bool FAST>
 __global__ void __launch_bounds__(GN_THREADS) gn_bwd_reduce_kernel(PuGnBwdArgs a, int rows) {
-    extern __shared__ float sm[];
+    extern __shared__ float sm[];   // [C][2] block partial sums
     const PuGnArgs& f = a.f;
     const int C = f.C0 + f.C1, nvec = C / 8;
     const int n = blockIdx.y;
-    GnSmem s = gn_smem(sm, C);
-    float* red = sm + 4 * C;   // [C][2]
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
-    gn_setup(f, n, s);
     const int PL = GN_THREADS / nvec;
     const int v = threadIdx.x % nvec, pl = threadIdx.x / nvec;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
     const int HW = f.H * f.W;
     const int r0 = blockIdx.x * rows;
     int r1 = r0 + rows;
@@ -234,12 +256,14 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_reduce_kernel(PuGnBwdArgs a
     const T* dy = reinterpret_cast<const T*>(a.dy);
     if (pl < PL) {
         const int c0 = v * 8;
+        ChanConst k;
+        gn_load_consts(f, n, c0, k);
         float A[8], B[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) A[e] = B[e] = 0.f;
         for (int r = r0 + pl; r < r1; r += PL) {
             float xh[8], du[8];
-            gn_du8<T>(f, s, dy, n, r / f.W, r % f.W, c0, xh, du);
+            gn_du8<T, FAST>(f, k, dy, n, r, c0, xh, du);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 A[e] += du[e];
@@ -248,76 +272,80 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_reduce_kernel(PuGnBwdArgs a
         }
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            atomicAdd(&red[2 * (c0 + e)], A[e]);
-            atomicAdd(&red[2 * (c0 + e) + 1], B[e]);
+            atomicAdd(&sm[2 * (c0 + e)], A[e]);
+            atomicAdd(&sm[2 * (c0 + e) + 1], B[e]);
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(a.sums + (long long)n * C * 2 + i, red[i]);
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(a.sums + (long long)n * C * 2 + i, sm[i]);
 }
 
-template <typename T>
+template <typename T, bool FAST>
 __global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(PuGnBwdArgs a, int rows) {
-    extern __shared__ float sm[];
+    extern __shared__ float sm[];   // [G][2]: sum_c gamma' A, sum_c gamma' B
     const PuGnArgs& f = a.f;
     const int C = f.C0 + f.C1, nvec = C / 8, Cg = C / f.G;
     const int n = blockIdx.y;
-    GnSmem s = gn_smem(sm, C);
-    float* S = sm + 4 * C;   // [G][2]: sum_c gamma' A, sum_c gamma' B
-    for (int i = threadIdx.x; i < 2 * f.G; i += blockDim.x) S[i] = 0.f;
-    gn_setup(f, n, s);
+    const int PL = GN_THREADS / nvec;
+    const int v = threadIdx.x % nvec, pl = threadIdx.x / nvec;
+    for (int i = threadIdx.x; i < 2 * f.G; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float gam = f.gamma[c];
+        if (f.ada) gam *= 1.f + f.ada[c];
         const int g = c / Cg;
-        atomicAdd(&S[2 * g], s.gam[c] * a.sums[((long long)n * C + c) * 2]);
-        atomicAdd(&S[2 * g + 1], s.gam[c] * a.sums[((long long)n * C + c) * 2 + 1]);
+        atomicAdd(&sm[2 * g], gam * a.sums[((long long)n * C + c) * 2]);
+        atomicAdd(&sm[2 * g + 1], gam * a.sums[((long long)n * C + c) * 2 + 1]);
     }
     __syncthreads();
+    if (pl >= PL) return;
+    const int c0 = v * 8;
+    ChanConst k;
+    gn_load_consts(f, n, c0, k);
     const float inv_m = 1.f / ((float)Cg * (float)f.H * (float)f.W);
+    float s1[8], s2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int g = (c0 + e) / Cg;
+        s1[e] = sm[2 * g] * inv_m;
+        s2[e] = sm[2 * g + 1] * inv_m;
+    }
     const int HW = f.H * f.W;
     const int r0 = blockIdx.x * rows;
     int r1 = r0 + rows;
     if (r1 > HW) r1 = HW;
     const T* dy = reinterpret_cast<const T*>(a.dy);
     const T* dres = reinterpret_cast<const T*>(a.dres);
-    T* dx0 = reinterpret_cast<T*>(a.dx0);
-    T* dx1 = reinterpret_cast<T*>(a.dx1);
-    const int total = (r1 - r0) * nvec;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int v = idx % nvec;
-        const int r = r0 + idx / nvec;
-        const int iy = r / f.W, ix = r % f.W;
-        const int c0 = v * 8;
+    T* dst;
+    int stride, acc;
+    if (c0 < f.C0) {
+        dst = reinterpret_cast<T*>(a.dx0) + (long long)n * HW * f.C0 + c0;
+        stride = f.C0;
+        acc = a.acc0;
+    } else {
+        dst = reinterpret_cast<T*>(a.dx1) + (long long)n * HW * f.C1 + (c0 - f.C0);
+        stride = f.C1;
+        acc = a.acc1;
+    }
+    for (int r = r0 + pl; r < r1; r += PL) {
         float xh[8], du[8], o[8];
-        gn_du8<T>(f, s, dy, n, iy, ix, c0, xh, du);
+        gn_du8<T, FAST>(f, k, dy, n, r, c0, xh, du);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int g = (c0 + e) / Cg;
-            const float dxh = du[e] * s.gam[c0 + e];
-            o[e] = s.rstd[c0 + e] * (dxh - S[2 * g] * inv_m - xh[e] * S[2 * g + 1] * inv_m);
-        }
+        for (int e = 0; e < 8; ++e) o[e] = k.rstd[e] * (du[e] * k.gam[e] - s1[e] - xh[e] * s2[e]);
         if (dres) {
             float d[8];
-            gn_gather8<T>(dres, a.dres_resample, n, f.H, f.W, iy, ix, C, c0, d);
+            gn_gather8<T>(dres, a.dres_resample, n, f.H, f.W, r, C, c0, d);
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] += d[e];
         }
-        const long long pix = (long long)n * HW + r;
-        T* dst;
-        int acc;
-        if (c0 < f.C0) {
-            dst = dx0 + pix * f.C0 + c0;
-            acc = a.acc0;
-        } else {
-            dst = dx1 + pix * f.C1 + (c0 - f.C0);
-            acc = a.acc1;
-        }
+        T* p = dst + (long long)r * stride;
         if (acc) {
             float old[8];
-            ld8(dst, old);
+            ld8(p, old);
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] += old[e];
         }
-        st8(dst, o);
+        st8(p, o);
     }
 }
 
@@ -352,6 +380,7 @@ __global__ void gn_bwd_params_kernel(PuGnBwdArgs a) {
     }
 }
 
+// pixel rows per block: aim at ~8 blocks per SM over the whole launch, but at least `min_rows` rows of work
 static int rows_per_block(int HW, int N, int min_rows) {
     int target_blocks = (148 * 8) / (N > 0 ? N : 1);
     if (target_blocks < 1) target_blocks = 1;
@@ -389,7 +418,7 @@ int pu_gn_stats(const void* src0, const void* src1, int C0, int C1, int N, int H
     cudaStream_t st = (cudaStream_t)stream;
     PU_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * N * G, st));
     const int PL = GN_THREADS / (C / 8);
-    const int rows = rows_per_block(HW, N, PL * 4);
+    const int rows = rows_per_block(HW, N, PL * 8);
     dim3 grid(cdiv(HW, rows), N);
     const size_t smem = sizeof(float) * 2 * G;
     if (dtype == PU_F32)
@@ -410,13 +439,13 @@ int pu_gn_apply(const PuGnArgs* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int C = a->C0 + a->C1;
     const int OHW = a->resample == PU_RS_UP ? a->H * a->W * 4 : (a->resample == PU_RS_DOWN ? a->H * a->W / 4 : a->H * a->W);
-    const int rows = rows_per_block(OHW, a->N, 8);
+    const int PL = GN_THREADS / (C / 8);
+    const int rows = rows_per_block(OHW, a->N, PL * 8);
     dim3 grid(cdiv(OHW, rows), a->N);
-    const size_t smem = sizeof(float) * 4 * C;
     if (a->dtype == PU_F32)
-        gn_apply_kernel<float><<<grid, GN_THREADS, smem, st>>>(*a, rows);
+        gn_apply_kernel<float, false><<<grid, GN_THREADS, 0, st>>>(*a, rows);
     else
-        gn_apply_kernel<__nv_bfloat16><<<grid, GN_THREADS, smem, st>>>(*a, rows);
+        gn_apply_kernel<__nv_bfloat16, true><<<grid, GN_THREADS, 0, st>>>(*a, rows);
     return check_launch("gn_apply");
 }
 
@@ -432,25 +461,23 @@ int pu_gn_bwd(const PuGnBwdArgs* a, void* stream) {
     const int HW = f.H * f.W;
     PU_CUDA(cudaMemsetAsync(a->sums, 0, sizeof(float) * 2 * f.N * C, st));
     const int PL = GN_THREADS / (C / 8);
+    const int rows = rows_per_block(HW, f.N, PL * 8);
+    dim3 grid(cdiv(HW, rows), f.N);
     {
-        const int rows = rows_per_block(HW, f.N, PL * 4);
-        dim3 grid(cdiv(HW, rows), f.N);
-        const size_t smem = sizeof(float) * 6 * C;
+        const size_t smem = sizeof(float) * 2 * C;
         if (f.dtype == PU_F32)
-            gn_bwd_reduce_kernel<float><<<grid, GN_THREADS, smem, st>>>(*a, rows);
+            gn_bwd_reduce_kernel<float, false><<<grid, GN_THREADS, smem, st>>>(*a, rows);
         else
-            gn_bwd_reduce_kernel<__nv_bfloat16><<<grid, GN_THREADS, smem, st>>>(*a, rows);
+            gn_bwd_reduce_kernel<__nv_bfloat16, true><<<grid, GN_THREADS, smem, st>>>(*a, rows);
         rc = check_launch("gn_bwd_reduce");
         if (rc) return rc;
     }
     {
-        const int rows = rows_per_block(HW, f.N, 8);
-        dim3 grid(cdiv(HW, rows), f.N);
-        const size_t smem = sizeof(float) * (4 * C + 2 * f.G);
+        const size_t smem = sizeof(float) * 2 * f.G;
         if (f.dtype == PU_F32)
-            gn_bwd_apply_kernel<float><<<grid, GN_THREADS, smem, st>>>(*a, rows);
+            gn_bwd_apply_kernel<float, false><<<grid, GN_THREADS, smem, st>>>(*a, rows);
         else
-            gn_bwd_apply_kernel<__nv_bfloat16><<<grid, GN_THREADS, smem, st>>>(*a, rows);
+            gn_bwd_apply_kernel<__nv_bfloat16, true><<<grid, GN_THREADS, smem, st>>>(*a, rows);
         rc = check_launch("gn_bwd_apply");
         if (rc) return rc;
     }

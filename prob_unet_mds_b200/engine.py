@@ -158,9 +158,9 @@ class UNetEngine:
     # ---- backward ---------------------------------------------------------------------------------------------------
     def _wgrad(self, grads, param, src0, dy, k, src1=None, perm=None):
         dwp = ops.conv2d_wgrad(src0, dy, k, src1=src1)
-        g = torch.empty_like(param)
+        g = grads.alloc(param)          # a view into an all-reduce bucket under data parallelism
         ops.unpack_wgrad(dwp, g, perm=perm)
-        grads[id(param)] = g
+        grads[id(param)] = g            # "written": may trigger the bucket's all-reduce
 
     def backward(self, tape, dfeat, grads):
         """dfeat: NHWC gradient wrt the features.  Fills grads[id(param)] for every live parameter."""
@@ -255,8 +255,14 @@ class UNetEngine:
             gbuf[id(xb)] = dxb
 
 
-def _unet_param_list(unet):
-    return [p for p in unet.parameters()]
+def new_grad_sink(model):
+    """Where backward puts parameter gradients: plain tensors, or all-reduce buckets when parallel.DataParallel is
+    attached to the model."""
+    factory = getattr(model, '_grad_sink_factory', None)
+    if factory is not None:
+        return factory()
+    from .parallel import GradSink
+    return GradSink()
 
 
 def _collect_grads(params, grads, zero_cache):
@@ -291,7 +297,9 @@ class _UNetFunction(torch.autograd.Function):
         unet = ctx.unet
         eng = unet.engine()
         dfeat = ops.nchw_to_nhwc(dout.contiguous().float(), eng.dtype)
-        grads = eng.backward(ctx.tape, dfeat, {})
+        grads = new_grad_sink(unet)
+        eng.backward(ctx.tape, dfeat, grads)
+        grads.finish()
         ctx.tape = None
         named = list(unet.named_parameters())
         if not hasattr(unet, '_zero_cache'):
@@ -380,7 +388,7 @@ class GaussianEngine:
             else:
                 dr = ops.relu_pool_bwd(dp, r)
             dwp = ops.conv2d_wgrad(x, dr, 3)
-            g = torch.empty_like(c.weight)
+            g = grads.alloc(c.weight)
             ops.unpack_wgrad(dwp, g)
             grads[id(c.weight)] = g
             grads[id(c.bias)] = ops.bias_grad(dr)

@@ -268,7 +268,7 @@ class _ElboFunction(torch.autograd.Function):
         ctx.saved = None
         dt = model.compute_dtype
         dev = s['feat'].device
-        grads = {}
+        grads = engine.new_grad_sink(model)
         fc = model.fcomb
         w0p, b0p, w1p, b1p, w2p, b2p = fc.params()
         w0, w1, w2 = w0p.detach(), w1p.detach(), w2p.detach()
@@ -308,5 +308,6 @@ class _ElboFunction(torch.autograd.Function):
         model.posterior.engine(dt).backward(s['qtape'], dmu_q, dls_q, grads)
         model.prior.engine(dt).backward(s['ptape'], dmu_p, dls_p, grads)
         model.unet.engine().backward(s['utape'], dfeat, grads)
+        grads.finish()
         named = model._named()
         return (None, None, None) + tuple(engine._collect_grads(named, grads, model._zero_cache))

@@ -1,0 +1,86 @@
+"""Per-layer microbenchmark of the tcgen05 conv kernels (forward/dgrad and wgrad) and attention at the shapes one
+ELBO step issues, batch 64.  CUDA events on the launching stream, L2 flushed between reps by
+the size of the working set (every tensor here is >> 126 MB at batch 64 except the 16x16 level)."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from prob_unet_mds_b200 import _lib as L  # noqa: E402
+from prob_unet_mds_b200 import ops  # noqa: E402
+
+B = int(os.environ.get('B', '64'))
+REPS = 5
+# (Cin0, Cin1, Cout, HW, k, count)
+CONV_SHAPES = [
+    (128, 0, 128, 128, 3, 7), (256, 0, 128, 128, 3, 2), (256, 0, 256, 128, 3, 2), (384, 0, 128, 128, 3, 1),
+    (128, 0, 64, 128, 3, 1),
+    (128, 0, 256, 64, 3, 1), (256, 0, 256, 64, 3, 6), (384, 0, 256, 64, 3, 1), (384, 0, 384, 64, 3, 2),
+    (512, 0, 256, 64, 3, 1), (640, 0, 256, 64, 3, 1),
+    (256, 0, 384, 32, 3, 1), (384, 0, 384, 32, 3, 6), (512, 0, 512, 32, 3, 2), (768, 0, 384, 32, 3, 3),
+    (384, 0, 512, 16, 3, 1), (512, 0, 512, 16, 3, 10), (1024, 0, 512, 16, 3, 3),
+    (256, 0, 768, 64, 1, 5), (256, 0, 256, 64, 1, 5), (384, 0, 1152, 32, 1, 5), (512, 0, 1536, 16, 1, 6),
+    (256, 128, 128, 128, 1, 2),
+]
+
+
+def timeit(fn):
+    fn()
+    torch.cuda.synchronize()
+    s = torch.cuda.Event(enable_timing=True)
+    e = torch.cuda.Event(enable_timing=True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+    ms = []
+    for _ in range(REPS):
+        flush.zero_()
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ms.append(s.elapsed_time(e))
+    return min(ms)
+
+
+def main():
+    dt = torch.bfloat16
+    rows = []
+    tot = {'fwd': [0.0, 0.0], 'dgrad': [0.0, 0.0], 'wgrad': [0.0, 0.0]}
+    for c0, c1, co, hw, k, cnt in CONV_SHAPES:
+        x0 = torch.randn(B, hw, hw, c0, device='cuda').to(dt)
+        x1 = torch.randn(B, hw, hw, c1, device='cuda').to(dt) if c1 else None
+        dy = torch.randn(B, hw, hw, co, device='cuda').to(dt)
+        w = torch.randn(co, c0 + c1, k, k, device='cuda') * 0.02
+        wf = ops.pack_weight(w, 0, dt)
+        wd = ops.pack_weight(w, 1, dt)
+        bias = torch.randn(co, device='cuda')
+        flops = 2.0 * B * hw * hw * co * k * k * (c0 + c1)
+        t_f = timeit(lambda: ops.conv2d(x0, wf, co, k, bias=bias, src1=x1, flags=L.CONV_FORCE_TC))
+        t_d = timeit(lambda: ops.conv2d(dy, wd, c0 + c1, k, flags=L.CONV_FORCE_TC))
+        t_w = timeit(lambda: ops.conv2d_wgrad(x0, dy, k, src1=x1, flags=L.CONV_FORCE_TC))
+        rows.append(dict(shape=f'{c0}+{c1}->{co} {hw}x{hw} k{k} x{cnt}', fwd_ms=round(t_f, 3), dgrad_ms=round(t_d, 3),
+                         wgrad_ms=round(t_w, 3), fwd_tf=round(flops / t_f / 1e9, 1), dgrad_tf=round(flops / t_d / 1e9, 1),
+                         wgrad_tf=round(flops / t_w / 1e9, 1)))
+        for key, t in (('fwd', t_f), ('dgrad', t_d), ('wgrad', t_w)):
+            tot[key][0] += flops * cnt
+            tot[key][1] += t * cnt
+        print(json.dumps(rows[-1]), flush=True)
+        del x0, x1, dy
+    for key, (fl, ms) in tot.items():
+        print(f'{key}: {ms:.2f} ms per step-equivalent, {fl / ms / 1e9:.1f} TFLOP/s')
+    # attention
+    for heads, T, cnt in ((4, 4096, 5), (6, 1024, 5), (8, 256, 6)):
+        C = heads * 64
+        qkv = torch.randn(B, T, 3 * C, device='cuda').to(dt)
+        out, lse = ops.attention_fwd(qkv, heads)
+        dout = torch.randn_like(out)
+        fl = 4.0 * B * heads * T * T * 64
+        t_f = timeit(lambda: ops.attention_fwd(qkv, heads))
+        t_b = timeit(lambda: ops.attention_bwd(qkv, out, dout, lse, heads))
+        print(json.dumps(dict(shape=f'attn heads={heads} T={T} x{cnt}', fwd_ms=round(t_f, 3), bwd_ms=round(t_b, 3),
+                              fwd_tf=round(fl / t_f / 1e9, 1), bwd_tf=round(2.5 * fl / t_b / 1e9, 1))), flush=True)
+
+
+if __name__ == '__main__':
+    main()
