@@ -125,7 +125,7 @@ typedef struct PuGnBwdArgs {
     const void* dy;       /* gradient wrt y, at the resampled resolution                               */
     const void* dres;     /* optional extra gradient added to dx (skip path), layout per dres_resample */
     int dres_resample;    /* PU_RS_NONE: dres is [N,H,W,C]; else it is at y's resolution               */
-    float* sums;          /* workspace [N][C][2] fp32 (sum du, sum du*xhat)                            */
+    double* sums;         /* workspace [N][C][2] fp64 (sum du, sum du*xhat)                            */
     void* dx0;            /* gradient wrt src0 [N,H,W,C0]                                              */
     void* dx1;            /* gradient wrt src1 [N,H,W,C1] or NULL                                      */
     int acc0, acc1;       /* 1: dx += ...                                                              */

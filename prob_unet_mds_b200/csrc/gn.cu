@@ -241,13 +241,15 @@ __device__ __forceinline__ void gn_du8(const PuGnArgs& f, const ChanConst& k, co
 
 template <typename T, bool FAST>
 __global__ void __launch_bounds__(GN_THREADS) gn_bwd_reduce_kernel(PuGnBwdArgs a, int rows) {
-    extern __shared__ float sm[];   // [C][2] block partial sums
+    // [C][2] block partial sums.  fp64: these sums cancel heavily (sum of signed terms), fp32 atomics made the
+    // parameter gradients depend on the block scheduling order at the 1e-3 level.
+    extern __shared__ double smd[];
     const PuGnArgs& f = a.f;
     const int C = f.C0 + f.C1, nvec = C / 8;
     const int n = blockIdx.y;
     const int PL = GN_THREADS / nvec;
     const int v = threadIdx.x % nvec, pl = threadIdx.x / nvec;
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) smd[i] = 0.0;
     __syncthreads();
     const int HW = f.H * f.W;
     const int r0 = blockIdx.x * rows;
@@ -272,43 +274,43 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_reduce_kernel(PuGnBwdArgs a
         }
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            atomicAdd(&sm[2 * (c0 + e)], A[e]);
-            atomicAdd(&sm[2 * (c0 + e) + 1], B[e]);
+            atomicAdd(&smd[2 * (c0 + e)], (double)A[e]);
+            atomicAdd(&smd[2 * (c0 + e) + 1], (double)B[e]);
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(a.sums + (long long)n * C * 2 + i, sm[i]);
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(a.sums + (long long)n * C * 2 + i, smd[i]);
 }
 
 template <typename T, bool FAST>
 __global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(PuGnBwdArgs a, int rows) {
-    extern __shared__ float sm[];   // [G][2]: sum_c gamma' A, sum_c gamma' B
+    extern __shared__ double smd[];   // [G][2]: sum_c gamma' A, sum_c gamma' B
     const PuGnArgs& f = a.f;
     const int C = f.C0 + f.C1, nvec = C / 8, Cg = C / f.G;
     const int n = blockIdx.y;
     const int PL = GN_THREADS / nvec;
     const int v = threadIdx.x % nvec, pl = threadIdx.x / nvec;
-    for (int i = threadIdx.x; i < 2 * f.G; i += blockDim.x) sm[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * f.G; i += blockDim.x) smd[i] = 0.0;
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float gam = f.gamma[c];
         if (f.ada) gam *= 1.f + f.ada[c];
         const int g = c / Cg;
-        atomicAdd(&sm[2 * g], gam * a.sums[((long long)n * C + c) * 2]);
-        atomicAdd(&sm[2 * g + 1], gam * a.sums[((long long)n * C + c) * 2 + 1]);
+        atomicAdd(&smd[2 * g], (double)gam * a.sums[((long long)n * C + c) * 2]);
+        atomicAdd(&smd[2 * g + 1], (double)gam * a.sums[((long long)n * C + c) * 2 + 1]);
     }
     __syncthreads();
     if (pl >= PL) return;
     const int c0 = v * 8;
     ChanConst k;
     gn_load_consts(f, n, c0, k);
-    const float inv_m = 1.f / ((float)Cg * (float)f.H * (float)f.W);
+    const double inv_m = 1.0 / ((double)Cg * (double)f.H * (double)f.W);
     float s1[8], s2[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         const int g = (c0 + e) / Cg;
-        s1[e] = sm[2 * g] * inv_m;
-        s2[e] = sm[2 * g + 1] * inv_m;
+        s1[e] = (float)(smd[2 * g] * inv_m);
+        s2[e] = (float)(smd[2 * g + 1] * inv_m);
     }
     const int HW = f.H * f.W;
     const int r0 = blockIdx.x * rows;
@@ -354,11 +356,12 @@ __global__ void gn_bwd_params_kernel(PuGnBwdArgs a) {
     const int C = f.C0 + f.C1;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
-    float sa = 0.f, sb = 0.f;
+    double sad = 0.0, sbd = 0.0;
     for (int n = 0; n < f.N; ++n) {
-        sa += a.sums[((long long)n * C + c) * 2];
-        sb += a.sums[((long long)n * C + c) * 2 + 1];
+        sad += a.sums[((long long)n * C + c) * 2];
+        sbd += a.sums[((long long)n * C + c) * 2 + 1];
     }
+    const float sa = (float)sad, sb = (float)sbd;
     const float sc = f.ada ? f.ada[c] : 0.f;
     const float dg = (1.f + sc) * sb, db = (1.f + sc) * sa;
     if (a.acc_params) {
@@ -459,12 +462,12 @@ int pu_gn_bwd(const PuGnBwdArgs* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int C = f.C0 + f.C1;
     const int HW = f.H * f.W;
-    PU_CUDA(cudaMemsetAsync(a->sums, 0, sizeof(float) * 2 * f.N * C, st));
+    PU_CUDA(cudaMemsetAsync(a->sums, 0, sizeof(double) * 2 * f.N * C, st));
     const int PL = GN_THREADS / (C / 8);
     const int rows = rows_per_block(HW, f.N, PL * 8);
     dim3 grid(cdiv(HW, rows), f.N);
     {
-        const size_t smem = sizeof(float) * 2 * C;
+        const size_t smem = sizeof(double) * 2 * C;
         if (f.dtype == PU_F32)
             gn_bwd_reduce_kernel<float, false><<<grid, GN_THREADS, smem, st>>>(*a, rows);
         else
@@ -473,7 +476,7 @@ int pu_gn_bwd(const PuGnBwdArgs* a, void* stream) {
         if (rc) return rc;
     }
     {
-        const size_t smem = sizeof(float) * 2 * f.G;
+        const size_t smem = sizeof(double) * 2 * f.G;
         if (f.dtype == PU_F32)
             gn_bwd_apply_kernel<float, false><<<grid, GN_THREADS, smem, st>>>(*a, rows);
         else

@@ -153,7 +153,7 @@ def gn_bwd(src0, stats, gamma, beta, dy, dgamma, dbeta, src1=None, ada=None, dad
     if src1 is not None and dx1 is None:
         dx1 = torch.empty_like(src1)
         acc1 = False
-    sums = torch.empty((N, C0 + C1, 2), dtype=torch.float32, device=src0.device)
+    sums = torch.empty((N, C0 + C1, 2), dtype=torch.float64, device=src0.device)
     f = _gn_args(src0, src1, stats, gamma, beta, ada, silu, resample, dropout_p, seed, None, eps)
     a = L.PuGnBwdArgs(f, ptr(dy), ptr(dres), dres_resample, ptr(sums), ptr(dx0), ptr(dx1), int(acc0), int(acc1),
                       ptr(dgamma), ptr(dbeta), ptr(dada), int(acc_params))
