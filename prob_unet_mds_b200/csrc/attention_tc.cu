@@ -259,6 +259,236 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParam
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// forward, two query tiles per CTA (256 rows): the K/V tiles are loaded once and used by both q tiles, and two
+// softmax warpgroups (warps 4-7 -> q tile 0, warps 8-11 -> q tile 1) keep the MUFU busy while the tensor core
+// works for the other tile.  TMEM: S0 | S1 (128 cols each) | O0 | O1 (64 cols each).  Used when T % 256 == 0.
+// ------------------------------------------------------------------------------------------------
+constexpr int A2_KV_STAGES = 3;
+constexpr int A2_SMEM = 2 * AT_TILE /*Q0,Q1*/ + A2_KV_STAGES * 2 * AT_TILE /*K,V*/ + 2 * 2 * AT_TILE /*P0,P1*/ + 1024 + 256;
+
+__global__ void __launch_bounds__(384, 1)
+attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;                                        // q tile t at + t*TILE
+    uint8_t* sKV = sQ + 2 * AT_TILE;                           // stage s: K at +s*2*TILE, V at +s*2*TILE + TILE
+    uint8_t* sP = sKV + A2_KV_STAGES * 2 * AT_TILE;            // q tile t at + t*2*TILE (two 64-key blocks)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * 2 * AT_TILE);
+    uint64_t* q_full = bars;                       // 1
+    uint64_t* kv_full = bars + 1;                  // [2]
+    uint64_t* kv_empty = kv_full + A2_KV_STAGES;   // [2]
+    uint64_t* s_full = kv_empty + A2_KV_STAGES;    // [2] per q tile
+    uint64_t* s_empty = s_full + 2;
+    uint64_t* p_full = s_empty + 2;
+    uint64_t* o_full = p_full + 2;
+    uint64_t* o_empty = o_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nh = blockIdx.y, n = nh / p.heads, h = nh % p.heads;
+    const int q0 = blockIdx.x * 2 * AT_TQ;
+    const int ntiles = p.T / AT_TK;
+    const int row_base = n * p.T;
+    const int colQ = h * AT_D, colK = p.C + h * AT_D, colV = 2 * p.C + h * AT_D;
+
+    if (warp == 0 && lane == 0) prefetch_tmap(&tmQKV);
+    if (warp == 1 && lane == 0) {
+        mbar_init(smem_u32(q_full), 1);
+        for (int s = 0; s < A2_KV_STAGES; ++s) {
+            mbar_init(smem_u32(&kv_full[s]), 1);
+            mbar_init(smem_u32(&kv_empty[s]), 1);
+        }
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(smem_u32(&s_full[t]), 1);
+            mbar_init(smem_u32(&s_empty[t]), 4);
+            mbar_init(smem_u32(&p_full[t]), 4);
+            mbar_init(smem_u32(&o_full[t]), 1);
+            mbar_init(smem_u32(&o_empty[t]), 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(smem_u32(tmem_slot), 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    const uint32_t tS = tmem_base;           // S[t] at + t*128
+    const uint32_t tO = tmem_base + 256;     // O[t] at + t*64
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(smem_u32(q_full), 2 * AT_TILE);
+            tma_load_2d(smem_u32(sQ), &tmQKV, smem_u32(q_full), colQ, row_base + q0);
+            tma_load_2d(smem_u32(sQ + AT_TILE), &tmQKV, smem_u32(q_full), colQ, row_base + q0 + AT_TQ);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int j = 0; j < ntiles; ++j) {
+                mbar_wait(smem_u32(&kv_empty[stage]), phase ^ 1);
+                const uint32_t fb = smem_u32(&kv_full[stage]);
+                mbar_expect_tx(fb, 2 * AT_TILE);
+                tma_load_2d(smem_u32(sKV + stage * 2 * AT_TILE), &tmQKV, fb, colK, row_base + j * AT_TK);
+                tma_load_2d(smem_u32(sKV + stage * 2 * AT_TILE + AT_TILE), &tmQKV, fb, colV, row_base + j * AT_TK);
+                if (++stage == A2_KV_STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t IDESC_S = idesc_bf16_f32(128, 128, 0, 0);
+            constexpr uint32_t IDESC_O = idesc_bf16_f32(128, 64, 0, 1);
+            mbar_wait(smem_u32(q_full), 0);
+            auto issue_s = [&](int t, uint32_t k_addr) {
+                const uint32_t q_addr = smem_u32(sQ + t * AT_TILE);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    mma_f16_ss(tS + t * 128, smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                               smem_desc_sw128(k_addr + k * 32, 16, 1024), IDESC_S, k ? 1u : 0u);
+                mma_commit(smem_u32(&s_full[t]));
+            };
+            int stage = 0;
+            uint32_t phase = 0;
+            mbar_wait(smem_u32(&kv_full[0]), 0);
+            tc_fence_after();
+            issue_s(0, smem_u32(sKV));
+            issue_s(1, smem_u32(sKV));
+            for (int j = 0; j < ntiles; ++j) {
+                const uint32_t jp = j & 1;
+                const uint32_t v_addr = smem_u32(sKV + stage * 2 * AT_TILE + AT_TILE);
+                int nstage = stage + 1;
+                uint32_t nphase = phase;
+                if (nstage == A2_KV_STAGES) {
+                    nstage = 0;
+                    nphase ^= 1;
+                }
+                const bool more = j + 1 < ntiles;
+                if (more) mbar_wait(smem_u32(&kv_full[nstage]), nphase);
+                for (int t = 0; t < 2; ++t) {
+                    // P_j written and S_j consumed by warpgroup t: first refill S (next keys), then O_j = P_j V_j
+                    mbar_wait(smem_u32(&p_full[t]), jp);
+                    mbar_wait(smem_u32(&s_empty[t]), jp);
+                    tc_fence_after();
+                    if (more) issue_s(t, smem_u32(sKV + nstage * 2 * AT_TILE));
+                    mbar_wait(smem_u32(&o_empty[t]), jp ^ 1);
+                    tc_fence_after();
+                    const uint32_t p_addr = smem_u32(sP + t * 2 * AT_TILE);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        mma_f16_ss(tO + t * 64, smem_desc_sw128(p_addr + (k >> 2) * AT_TILE + (k & 3) * 32, 16, 1024),
+                                   smem_desc_sw128(v_addr + k * 2048, 8192, 1024), IDESC_O, k ? 1u : 0u);
+                    mma_commit(smem_u32(&o_full[t]));
+                }
+                mma_commit(smem_u32(&kv_empty[stage]));
+                stage = nstage;
+                phase = nphase;
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        const int t = (warp - 4) >> 2;                     // q tile of this warpgroup
+        const int r = q * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        const float sc = 0.125f * 1.4426950408889634f;
+        float m = -INFINITY, l = 0.f;
+        float acc[AT_D];
+#pragma unroll
+        for (int d = 0; d < AT_D; ++d) acc[d] = 0.f;
+        uint8_t* pb = sP + t * 2 * AT_TILE;
+        float corr_prev = 1.f;
+        // acc = acc * corr + O_jj, with O_jj read back from TMEM (also means P_jj has been consumed by the MMA)
+        auto accumulate = [&](int jj, float corr) {
+            mbar_wait(smem_u32(&o_full[t]), jj & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < AT_D; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(tO + lane_off + t * 64 + c, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[c + i] = fmaf(acc[c + i], corr, __uint_as_float(v[i]));
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&o_empty[t]));
+        };
+        for (int j = 0; j < ntiles; ++j) {
+            const uint32_t jp = j & 1;
+            mbar_wait(smem_u32(&s_full[t]), jp);
+            tc_fence_after();
+            float mx = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < AT_TK; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(tS + lane_off + t * 128 + c, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+            }
+            const float m_new = fmaxf(m, mx * sc);
+            const float corr = ex2_approx(m - m_new);
+            // O_{j-1} (issued while the row max above was being computed) must be folded in before P is overwritten
+            if (j > 0) accumulate(j - 1, corr_prev);
+            corr_prev = corr;
+            float rs = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < AT_TK; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(tS + lane_off + t * 128 + c, v);
+                tc_wait_ld();
+                float pv[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    pv[i] = ex2_approx(fmaf(__uint_as_float(v[i]), sc, -m_new));
+                    rs += pv[i];
+                }
+                uint8_t* kb_base = pb + (c >> 6) * AT_TILE + r * 128;
+                const int chunk0 = (c & 63) >> 3;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint4 pk;
+                    __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) hp[e] = __floats2bfloat162_rn(pv[g * 8 + 2 * e], pv[g * 8 + 2 * e + 1]);
+                    *reinterpret_cast<uint4*>(kb_base + (((chunk0 + g) ^ (r & 7)) << 4)) = pk;
+                }
+            }
+            l = l * corr + rs;
+            m = m_new;
+            tc_fence_before();
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(smem_u32(&s_empty[t]));
+                mbar_arrive(smem_u32(&p_full[t]));
+            }
+        }
+        accumulate(ntiles - 1, corr_prev);
+        const float inv = 1.f / l;
+        const long long row = (long long)row_base + q0 + t * AT_TQ + r;
+        __nv_bfloat16* op = p.out + row * p.C + h * AT_D;
+#pragma unroll
+        for (int d = 0; d < AT_D; d += 8) {
+            float o8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o8[e] = acc[d + e] * inv;
+            st8(op + d, o8);
+        }
+        p.lse[((long long)n * p.heads + h) * p.T + q0 + t * AT_TQ + r] = (m + log2f(l)) * 0.6931471805599453f;
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 bool attention_tc_applicable(int N, int T, int heads, int dtype) {
     static int ok = -1;
     if (ok < 0) ok = pu_device_supports_tc();
@@ -279,6 +509,16 @@ int attention_fwd_tc(const void* qkv, void* out, float* lse, int N, int T, int h
     p.T = T; p.heads = heads; p.C = C;
     p.out = (__nv_bfloat16*)out;
     p.lse = lse;
+    if (T % (2 * AT_TQ) == 0) {
+        static bool attr2 = false;
+        if (!attr2) {
+            PU_CUDA(cudaFuncSetAttribute(attn_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM));
+            attr2 = true;
+        }
+        dim3 grid2(T / (2 * AT_TQ), N * heads);
+        attn_fwd_tc2_kernel<<<grid2, 384, A2_SMEM, st>>>(tm, p);
+        return check_launch("attn_fwd_tc2");
+    }
     dim3 grid(T / AT_TQ, N * heads);
     attn_fwd_tc_kernel<<<grid, 256, AT_SMEM, st>>>(tm, p);
     return check_launch("attn_fwd_tc");
@@ -293,8 +533,10 @@ int attention_fwd_tc(const void* qkv, void* out, float* lse, int N, int T, int h
 // dQ partial sums of the different key tiles are combined with vectorised fp32 reductions into dq_acc [N*T][C].
 // ------------------------------------------------------------------------------------------------
 constexpr int AB_QD_STAGES = 2;
+constexpr int AB_DQ_ROW = (AT_D + 4) * 4;     // fp32 dQ staging row: 64 floats + 16 B pad (bank-conflict-free v4 stores)
+constexpr int AB_DQ_BYTES = AT_TQ * AB_DQ_ROW;
 constexpr int AB_SMEM = 2 * AT_TILE /*K,V*/ + AB_QD_STAGES * 2 * AT_TILE /*Q,dO*/ + 2 * AT_TILE /*P*/ + 2 * AT_TILE /*dS*/ +
-                        1024 + 256;
+                        AB_DQ_BYTES + 1024 + 256;
 
 struct AttnBwdParams {
     int T, heads, C;
@@ -308,7 +550,7 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                    const AttnBwdParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -318,7 +560,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     uint8_t* sQD = sV + AT_TILE;                           // stage s: Q at +s*2*TILE, dO at +s*2*TILE + TILE
     uint8_t* sP = sQD + AB_QD_STAGES * 2 * AT_TILE;        // two 64-key blocks of [128 q][128 B]
     uint8_t* sDS = sP + 2 * AT_TILE;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + 2 * AT_TILE);
+    uint8_t* sDQ = sDS + 2 * AT_TILE;                      // fp32 [128][64 + 4] staging for the bulk reduction
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sDQ + AB_DQ_BYTES);
     uint64_t* kv_full = bars;
     uint64_t* qd_full = bars + 1;                          // [2]
     uint64_t* qd_empty = qd_full + AB_QD_STAGES;
@@ -346,9 +589,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             mbar_init(smem_u32(&qd_empty[s]), 1);
         }
         mbar_init(smem_u32(sdp_full), 1);
-        mbar_init(smem_u32(pds_full), 4);
+        mbar_init(smem_u32(pds_full), 8);    // one arrive per softmax warp (2 warpgroups x 4 warps)
         mbar_init(smem_u32(dq_full), 1);
-        mbar_init(smem_u32(dq_empty), 4);
+        mbar_init(smem_u32(dq_empty), 8);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -442,7 +685,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             }
         }
     } else if (warp >= 4) {
-        const int q = warp - 4;
+        // two softmax warpgroups (warps 4-7 and 8-11): both own query row r = TMEM lane r, warpgroup wg handles the
+        // 64-key block wg of S / dP (= shared-memory block wg of P / dS) and columns [32*wg, 32*wg+32) of dQ, dK, dV
+        const int q = warp & 3;
+        const int wg = (warp - 4) >> 2;
         const int r = q * 32 + lane;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
         const float sc = 0.125f * 1.4426950408889634f;
@@ -454,7 +700,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             mbar_wait(smem_u32(sdp_full), i & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < AT_TK; c += 32) {
+            for (int c = wg * 64; c < wg * 64 + 64; c += 32) {
                 uint32_t sv[32], dv[32];
                 tmem_ld32(tS + lane_off + c, sv);
                 tmem_ld32(tDP + lane_off + c, dv);
@@ -490,25 +736,35 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             mbar_wait(smem_u32(dq_full), i & 1);
             tc_fence_after();
             float* dst = p.dq_acc + ((long long)row_base + i * AT_TQ + r) * p.C + h * AT_D;
-#pragma unroll
-            for (int c = 0; c < AT_D; c += 32) {
+            {
+                // TMEM -> registers -> this thread's 128-byte half row of the fp32 staging tile -> one bulk
+                // reduce-add (TMA engine, fp32 atomics at L2) instead of 8 red.global.add.v4 instructions
+                const int c = wg * 32;
                 uint32_t v[32];
                 tmem_ld32(tDQ + lane_off + c, v);
+                // the previous trip's bulk reduction must have finished reading the staging row
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 tc_wait_ld();
+                uint8_t* srow = sDQ + r * AB_DQ_ROW + c * 4;
 #pragma unroll
                 for (int e = 0; e < 32; e += 4)
-                    red_add_v4(dst + c + e, __uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]),
-                               __uint_as_float(v[e + 3]));
+                    *reinterpret_cast<uint4*>(srow + e * 4) = make_uint4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+                fence_proxy_async();
+                asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], 128;" ::"l"(dst + c),
+                             "r"(smem_u32(srow))
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(dq_empty));
         }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all dQ reductions of this thread have landed
         // the last dq_full commit also covers the final dV / dK accumulation
         __nv_bfloat16* kp = p.dqkv + ((long long)row_base + k0 + r) * 3 * p.C + colK;
         __nv_bfloat16* vp = p.dqkv + ((long long)row_base + k0 + r) * 3 * p.C + colV;
-#pragma unroll
-        for (int c = 0; c < AT_D; c += 32) {
+        {
+            const int c = wg * 32;
             uint32_t a[32], b[32];
             tmem_ld32(tDK + lane_off + c, a);
             tmem_ld32(tDV + lane_off + c, b);
@@ -570,7 +826,7 @@ int attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const 
     p.lse = lse; p.delta = delta; p.dq_acc = dq_acc;
     p.dqkv = (__nv_bfloat16*)dqkv;
     dim3 grid(T / AT_TK, N * heads);
-    attn_bwd_tc_kernel<<<grid, 256, AB_SMEM, st>>>(tm, tmdo, p);
+    attn_bwd_tc_kernel<<<grid, 384, AB_SMEM, st>>>(tm, tmdo, p);
     rc = check_launch("attn_bwd_tc");
     if (rc) return rc;
     long long total = (long long)N * T * (C / 8);

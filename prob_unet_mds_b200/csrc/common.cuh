@@ -112,15 +112,17 @@ __device__ __forceinline__ uint4 philox4x32(uint2 key, uint4 ctr) {
 }
 // keep-mask bits for the 8 elements starting at element index `e8*8`
 __device__ __forceinline__ uint32_t dropout_keep8(unsigned long long seed, unsigned long long e8, float p) {
-    uint4 a = philox4x32(make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)),
-                         make_uint4((uint32_t)e8, (uint32_t)(e8 >> 32), 0x5eedu, 0u));
-    uint4 b = philox4x32(make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)),
-                         make_uint4((uint32_t)e8, (uint32_t)(e8 >> 32), 0x5eedu, 1u));
-    uint32_t thr = (uint32_t)(p * 4294967296.0f);  // drop when r < thr
-    uint32_t r[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    // one Philox call = 128 random bits = eight 16-bit uniforms (p is quantised to 1/65536)
+    const uint4 a = philox4x32(make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)),
+                               make_uint4((uint32_t)e8, (uint32_t)(e8 >> 32), 0x5eedu, 0u));
+    const uint32_t thr = (uint32_t)(p * 65536.0f);  // drop when r < thr
+    const uint32_t r[4] = {a.x, a.y, a.z, a.w};
     uint32_t m = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) m |= (r[i] >= thr ? 1u : 0u) << i;
+    for (int i = 0; i < 4; ++i) {
+        m |= ((r[i] & 0xffffu) >= thr ? 1u : 0u) << (2 * i);
+        m |= ((r[i] >> 16) >= thr ? 1u : 0u) << (2 * i + 1);
+    }
     return m;
 }
 

@@ -228,11 +228,22 @@ __global__ void __launch_bounds__(256) bias_grad_vec_kernel(const T* __restrict_
         float s[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) s[e] = 0.f;
-        for (long long p = p0 + pl; p < p1; p += PL) {
-            float x[8];
-            ld8(dy + p * C + v * 8, x);
+        for (long long p = p0 + pl; p < p1; p += 4 * PL) {
+            float x[4][8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) s[e] += x[e];
+            for (int j = 0; j < 4; ++j) {   // four independent 16-byte loads in flight
+                const long long pp = p + (long long)j * PL;
+                if (pp < p1) {
+                    ld8(dy + pp * C + v * 8, x[j]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) x[j][e] = 0.f;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) s[e] += x[j][e];
         }
 #pragma unroll
         for (int e = 0; e < 8; ++e) atomicAdd(&sm[v * 8 + e], s[e]);

@@ -57,6 +57,44 @@ __device__ __forceinline__ void gn_load_consts(const PuGnArgs& f, int n, int c0,
     }
 }
 
+// 8 channels exactly as loaded (kept packed so that several loads can be in flight per thread)
+template <typename T>
+struct Raw8;
+template <>
+struct Raw8<__nv_bfloat16> {
+    uint4 v;
+};
+template <>
+struct Raw8<float> {
+    float4 a, b;
+};
+__device__ __forceinline__ Raw8<__nv_bfloat16> ldraw(const __nv_bfloat16* p) {
+    Raw8<__nv_bfloat16> r;
+    r.v = *reinterpret_cast<const uint4*>(p);
+    return r;
+}
+__device__ __forceinline__ Raw8<float> ldraw(const float* p) {
+    Raw8<float> r;
+    r.a = *reinterpret_cast<const float4*>(p);
+    r.b = *reinterpret_cast<const float4*>(p + 4);
+    return r;
+}
+__device__ __forceinline__ void unpack(const Raw8<__nv_bfloat16>& r, float (&v)[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r.v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(h[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+    }
+}
+__device__ __forceinline__ void unpack(const Raw8<float>& r, float (&v)[8]) {
+    v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w;
+    v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+}
+
+constexpr int GN_NB = 2;   // independent 16-byte loads in flight per thread and array
+
 template <typename T>
 __device__ __forceinline__ void gn_load_x8(const PuGnArgs& f, long long pix, int c0, float (&v)[8]) {
     if (c0 < f.C0)
@@ -87,13 +125,23 @@ gn_stats_kernel(const T* __restrict__ s0, const T* __restrict__ s1, int C0, int 
         const int c0 = v * 8;
         const T* base = (c0 < C0) ? (s0 + (long long)n * HW * C0 + c0) : (s1 + (long long)n * HW * C1 + (c0 - C0));
         const int stride = (c0 < C0) ? C0 : C1;
-        for (int r = r0 + pl; r < r1; r += PL) {
-            float x[8];
-            ld8(base + (long long)r * stride, x);
+        for (int r = r0 + pl; r < r1; r += GN_NB * PL) {
+            Raw8<T> raw[GN_NB];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                s[e] += x[e];
-                q[e] = fmaf(x[e], x[e], q[e]);
+            for (int j = 0; j < GN_NB; ++j) {
+                const int rr = r + j * PL;
+                if (rr < r1) raw[j] = ldraw(base + (long long)rr * stride);
+            }
+#pragma unroll
+            for (int j = 0; j < GN_NB; ++j) {
+                if (r + j * PL >= r1) break;
+                float x[8];
+                unpack(raw[j], x);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    s[e] += x[e];
+                    q[e] = fmaf(x[e], x[e], q[e]);
+                }
             }
         }
         // combine channels of the same group before touching shared memory
@@ -120,7 +168,7 @@ gn_stats_kernel(const T* __restrict__ s0, const T* __restrict__ s1, int C0, int 
 
 // ---- forward apply ----
 template <typename T, bool FAST>
-__global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(PuGnArgs f, int rows) {
+__global__ void __launch_bounds__(GN_THREADS, 3) gn_apply_kernel(PuGnArgs f, int rows) {
     const int C = f.C0 + f.C1, nvec = C / 8;
     const int n = blockIdx.y;
     const int PL = GN_THREADS / nvec;
@@ -137,6 +185,46 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(PuGnArgs f, int ro
     const float inv_keep = f.dropout_p > 0.f ? 1.f / (1.f - f.dropout_p) : 1.f;
     T* y = reinterpret_cast<T*>(f.y) + (long long)n * OH * OW * C + c0;
     const long long in_base = (long long)n * f.H * f.W;
+    if (f.resample == PU_RS_NONE) {
+        // fast path: GN_NB pixels per trip, all loads issued before the first use
+        const T* xp;
+        int stride;
+        if (c0 < f.C0) {
+            xp = reinterpret_cast<const T*>(f.src0) + in_base * f.C0 + c0;
+            stride = f.C0;
+        } else {
+            xp = reinterpret_cast<const T*>(f.src1) + in_base * f.C1 + (c0 - f.C0);
+            stride = f.C1;
+        }
+        for (int op = r0 + pl; op < r1; op += GN_NB * PL) {
+            Raw8<T> raw[GN_NB];
+#pragma unroll
+            for (int j = 0; j < GN_NB; ++j) {
+                const int rr = op + j * PL;
+                if (rr < r1) raw[j] = ldraw(xp + (long long)rr * stride);
+            }
+#pragma unroll
+            for (int j = 0; j < GN_NB; ++j) {
+                const int rr = op + j * PL;
+                if (rr >= r1) break;
+                float x[8], o[8];
+                unpack(raw[j], x);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float u = fmaf((x[e] - k.mu[e]) * k.rstd[e], k.gam[e], k.bet[e]);
+                    o[e] = f.silu ? u * sigmoid_t<FAST>(u) : u;
+                }
+                if (f.dropout_p > 0.f) {
+                    const long long opix = in_base + rr;
+                    const uint32_t keep = dropout_keep8(f.seed, (unsigned long long)((opix * C + c0) >> 3), f.dropout_p);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] = ((keep >> e) & 1u) ? o[e] * inv_keep : 0.f;
+                }
+                st8(y + (long long)rr * C, o);
+            }
+        }
+        return;
+    }
     for (int op = r0 + pl; op < r1; op += PL) {
         float o[8];
         if (f.resample == PU_RS_NONE) {
@@ -211,6 +299,10 @@ __device__ __forceinline__ void gn_gather8(const T* dy, int rs, int n, int H, in
     }
 }
 
+template <bool FAST>
+__device__ __forceinline__ void gn_du8_calc(const PuGnArgs& f, const ChanConst& k, const float (&x)[8],
+                                            const float (&g)[8], long long pix, int c0, float (&xh)[8], float (&du)[8]);
+
 // du = d loss / d u  where u = xhat * gamma' + beta' and y = resample(dropout(act(u)))
 template <typename T, bool FAST>
 __device__ __forceinline__ void gn_du8(const PuGnArgs& f, const ChanConst& k, const T* dy, int n, int r, int c0,
@@ -220,6 +312,14 @@ __device__ __forceinline__ void gn_du8(const PuGnArgs& f, const ChanConst& k, co
     float x[8], g[8];
     gn_load_x8<T>(f, pix, c0, x);
     gn_gather8<T>(dy, f.resample, n, f.H, f.W, r, C, c0, g);
+    gn_du8_calc<FAST>(f, k, x, g, pix, c0, xh, du);
+}
+
+// same, from already loaded x (pre-norm activation) and g (gradient wrt the activation output, resample undone)
+template <bool FAST>
+__device__ __forceinline__ void gn_du8_calc(const PuGnArgs& f, const ChanConst& k, const float (&x)[8],
+                                            const float (&g)[8], long long pix, int c0, float (&xh)[8], float (&du)[8]) {
+    const int C = f.C0 + f.C1;
     uint32_t keep = 0xffu;
     float inv_keep = 1.f;
     if (f.dropout_p > 0.f) {
@@ -240,16 +340,16 @@ __device__ __forceinline__ void gn_du8(const PuGnArgs& f, const ChanConst& k, co
 }
 
 template <typename T, bool FAST>
-__global__ void __launch_bounds__(GN_THREADS) gn_bwd_reduce_kernel(PuGnBwdArgs a, int rows) {
-    // [C][2] block partial sums.  fp64: these sums cancel heavily (sum of signed terms), fp32 atomics made the
-    // parameter gradients depend on the block scheduling order at the 1e-3 level.
-    extern __shared__ double smd[];
+__global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_reduce_kernel(PuGnBwdArgs a, int rows) {
+    // [C][2] block partial sums: fp32 shared-memory atomics (native, fast) within the block, fp64 atomics across
+    // blocks (these sums cancel heavily -- signed terms -- so the long cross-block accumulation is done in fp64).
+    extern __shared__ float sm[];
     const PuGnArgs& f = a.f;
     const int C = f.C0 + f.C1, nvec = C / 8;
     const int n = blockIdx.y;
     const int PL = GN_THREADS / nvec;
     const int v = threadIdx.x % nvec, pl = threadIdx.x / nvec;
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) smd[i] = 0.0;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
     __syncthreads();
     const int HW = f.H * f.W;
     const int r0 = blockIdx.x * rows;
@@ -263,27 +363,67 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_reduce_kernel(PuGnBwdArgs a
         float A[8], B[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) A[e] = B[e] = 0.f;
-        for (int r = r0 + pl; r < r1; r += PL) {
-            float xh[8], du[8];
-            gn_du8<T, FAST>(f, k, dy, n, r, c0, xh, du);
+        if (f.resample == PU_RS_NONE) {
+            const long long base = (long long)n * HW;
+            const T* xp;
+            int stride;
+            if (c0 < f.C0) {
+                xp = reinterpret_cast<const T*>(f.src0) + base * f.C0 + c0;
+                stride = f.C0;
+            } else {
+                xp = reinterpret_cast<const T*>(f.src1) + base * f.C1 + (c0 - f.C0);
+                stride = f.C1;
+            }
+            const T* gp = dy + base * C + c0;
+            for (int r = r0 + pl; r < r1; r += GN_NB * PL) {
+                Raw8<T> xr[GN_NB], gr[GN_NB];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                A[e] += du[e];
-                B[e] = fmaf(du[e], xh[e], B[e]);
+                for (int j = 0; j < GN_NB; ++j) {
+                    const int rr = r + j * PL;
+                    if (rr < r1) {
+                        xr[j] = ldraw(xp + (long long)rr * stride);
+                        gr[j] = ldraw(gp + (long long)rr * C);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < GN_NB; ++j) {
+                    const int rr = r + j * PL;
+                    if (rr >= r1) break;
+                    float x[8], g[8], xh[8], du[8];
+                    unpack(xr[j], x);
+                    unpack(gr[j], g);
+                    gn_du8_calc<FAST>(f, k, x, g, base + rr, c0, xh, du);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        A[e] += du[e];
+                        B[e] = fmaf(du[e], xh[e], B[e]);
+                    }
+                }
+            }
+        } else {
+            for (int r = r0 + pl; r < r1; r += PL) {
+                float xh[8], du[8];
+                gn_du8<T, FAST>(f, k, dy, n, r, c0, xh, du);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    A[e] += du[e];
+                    B[e] = fmaf(du[e], xh[e], B[e]);
+                }
             }
         }
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            atomicAdd(&smd[2 * (c0 + e)], (double)A[e]);
-            atomicAdd(&smd[2 * (c0 + e) + 1], (double)B[e]);
+            atomicAdd(&sm[2 * (c0 + e)], A[e]);
+            atomicAdd(&sm[2 * (c0 + e) + 1], B[e]);
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(a.sums + (long long)n * C * 2 + i, smd[i]);
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x)
+        atomicAdd(a.sums + (long long)n * C * 2 + i, (double)sm[i]);
 }
 
 template <typename T, bool FAST>
-__global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(PuGnBwdArgs a, int rows) {
+__global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_apply_kernel(PuGnBwdArgs a, int rows) {
     extern __shared__ double smd[];   // [G][2]: sum_c gamma' A, sum_c gamma' B
     const PuGnArgs& f = a.f;
     const int C = f.C0 + f.C1, nvec = C / 8, Cg = C / f.G;
@@ -328,6 +468,52 @@ __global__ void __launch_bounds__(GN_THREADS) gn_bwd_apply_kernel(PuGnBwdArgs a,
         dst = reinterpret_cast<T*>(a.dx1) + (long long)n * HW * f.C1 + (c0 - f.C0);
         stride = f.C1;
         acc = a.acc1;
+    }
+    if (f.resample == PU_RS_NONE && (!dres || a.dres_resample == PU_RS_NONE)) {
+        constexpr int NB = 2;
+        const long long base = (long long)n * HW;
+        const T* xp = (c0 < f.C0) ? reinterpret_cast<const T*>(f.src0) + base * f.C0 + c0
+                                  : reinterpret_cast<const T*>(f.src1) + base * f.C1 + (c0 - f.C0);
+        const T* gp = dy + base * C + c0;
+        const T* rp = dres ? dres + base * C + c0 : nullptr;
+        for (int r = r0 + pl; r < r1; r += NB * PL) {
+            Raw8<T> xr[NB], gr[NB], rr_[NB], od[NB];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                const int rr = r + j * PL;
+                if (rr < r1) {
+                    xr[j] = ldraw(xp + (long long)rr * stride);
+                    gr[j] = ldraw(gp + (long long)rr * C);
+                    if (rp) rr_[j] = ldraw(rp + (long long)rr * C);
+                    if (acc) od[j] = ldraw(dst + (long long)rr * stride);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                const int rr = r + j * PL;
+                if (rr >= r1) break;
+                float x[8], g[8], xh[8], du[8], o[8];
+                unpack(xr[j], x);
+                unpack(gr[j], g);
+                gn_du8_calc<FAST>(f, k, x, g, base + rr, c0, xh, du);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = k.rstd[e] * (du[e] * k.gam[e] - s1[e] - xh[e] * s2[e]);
+                if (rp) {
+                    float d[8];
+                    unpack(rr_[j], d);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] += d[e];
+                }
+                if (acc) {
+                    float old[8];
+                    unpack(od[j], old);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] += old[e];
+                }
+                st8(dst + (long long)rr * stride, o);
+            }
+        }
+        return;
     }
     for (int r = r0 + pl; r < r1; r += PL) {
         float xh[8], du[8], o[8];
@@ -467,7 +653,7 @@ int pu_gn_bwd(const PuGnBwdArgs* a, void* stream) {
     const int rows = rows_per_block(HW, f.N, PL * 8);
     dim3 grid(cdiv(HW, rows), f.N);
     {
-        const size_t smem = sizeof(double) * 2 * C;
+        const size_t smem = sizeof(float) * 2 * C;
         if (f.dtype == PU_F32)
             gn_bwd_reduce_kernel<float, false><<<grid, GN_THREADS, smem, st>>>(*a, rows);
         else

@@ -43,7 +43,32 @@ def timeit(fn):
     return min(ms)
 
 
+def bench_gn():
+    dt = torch.bfloat16
+    for Cc, hw in ((128, 128), (256, 64), (384, 32), (1024, 16)):
+        x = torch.randn(B, hw, hw, Cc, device='cuda').to(dt)
+        dy = torch.randn(B, hw, hw, Cc, device='cuda').to(dt)
+        gamma = torch.ones(Cc, device='cuda')
+        beta = torch.zeros(Cc, device='cuda')
+        ada = torch.zeros(2 * Cc, device='cuda')
+        dg, db, da = torch.empty(Cc, device='cuda'), torch.empty(Cc, device='cuda'), torch.empty(2 * Cc, device='cuda')
+        st = ops.gn_stats(x)
+        nbytes = x.numel() * 2
+        t_s = timeit(lambda: ops.gn_stats(x))
+        t_a = timeit(lambda: ops.gn_apply(x, st, gamma, beta, ada=ada, silu=True, dropout_p=0.1, seed=1))
+        t_b = timeit(lambda: ops.gn_bwd(x, st, gamma, beta, dy, dg, db, ada=ada, dada=da, silu=True, dropout_p=0.1,
+                                        seed=1, dres=dy))
+        t_g = timeit(lambda: ops.bias_grad(dy))
+        print(json.dumps(dict(shape=f'gn C={Cc} {hw}x{hw}', stats_ms=round(t_s, 3), stats_gbs=round(nbytes / t_s / 1e6),
+                              apply_ms=round(t_a, 3), apply_gbs=round(2 * nbytes / t_a / 1e6),
+                              bwd_ms=round(t_b, 3), bwd_gbs=round(6 * nbytes / t_b / 1e6),
+                              bias_grad_ms=round(t_g, 3), bias_grad_gbs=round(nbytes / t_g / 1e6))), flush=True)
+
+
 def main():
+    if os.environ.get('ONLY') == 'gn':
+        return bench_gn()
+    bench_gn()
     dt = torch.bfloat16
     rows = []
     tot = {'fwd': [0.0, 0.0], 'dgrad': [0.0, 0.0], 'wgrad': [0.0, 0.0]}
