@@ -122,7 +122,8 @@ int pu_gn_apply(const PuGnArgs* a, void* stream);
 
 typedef struct PuGnBwdArgs {
     PuGnArgs f;           /* the forward call (y unused)                                               */
-    const void* dy;       /* gradient wrt y, at the resampled resolution                               */
+    const void* dy;       /* gradient wrt y, at the resampled resolution.  SCRATCH: when no resampling is */
+                          /* involved the buffer is overwritten (with d loss / d pre-activation)          */
     const void* dres;     /* optional extra gradient added to dx (skip path), layout per dres_resample */
     int dres_resample;    /* PU_RS_NONE: dres is [N,H,W,C]; else it is at y's resolution               */
     double* sums;         /* workspace [N][C][2] fp64 (sum du, sum du*xhat)                            */

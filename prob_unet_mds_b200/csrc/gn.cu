@@ -393,6 +393,9 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_reduce_kernel(PuGnBwdArg
                     unpack(xr[j], x);
                     unpack(gr[j], g);
                     gn_du8_calc<FAST>(f, k, x, g, base + rr, c0, xh, du);
+                    // dy is a scratch tensor in this mode: overwrite it with du so that the apply pass does not
+                    // have to redo the SiLU derivative and the dropout mask
+                    if (!a.dres || a.dres_resample == PU_RS_NONE) st8(const_cast<T*>(gp) + (long long)rr * C, du);
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         A[e] += du[e];
@@ -492,12 +495,14 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_apply_kernel(PuGnBwdArgs
             for (int j = 0; j < NB; ++j) {
                 const int rr = r + j * PL;
                 if (rr >= r1) break;
-                float x[8], g[8], xh[8], du[8], o[8];
+                float x[8], du[8], o[8];
                 unpack(xr[j], x);
-                unpack(gr[j], g);
-                gn_du8_calc<FAST>(f, k, x, g, base + rr, c0, xh, du);
+                unpack(gr[j], du);      // the reduce pass left du in the dy buffer
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = k.rstd[e] * (du[e] * k.gam[e] - s1[e] - xh[e] * s2[e]);
+                for (int e = 0; e < 8; ++e) {
+                    const float xh = (x[e] - k.mu[e]) * k.rstd[e];
+                    o[e] = k.rstd[e] * (du[e] * k.gam[e] - s1[e] - xh * s2[e]);
+                }
                 if (rp) {
                     float d[8];
                     unpack(rr_[j], d);
