@@ -616,8 +616,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
                 mbar_wait(smem_u32(&qd_empty[stage]), phase ^ 1);
                 const uint32_t fb = smem_u32(&qd_full[stage]);
                 mbar_expect_tx(fb, 2 * AT_TILE);
-                tma_load_2d(smem_u32(sQD + stage * 2 * AT_TILE), &tmQKV, fb, colQ, row_base + i * AT_TQ);
-                tma_load_2d(smem_u32(sQD + stage * 2 * AT_TILE + AT_TILE), &tmDO, fb, colQ, row_base + i * AT_TQ);
+                // q tiles are walked starting at this CTA's own key-tile index: concurrently running CTAs of one
+                // (sample, head) then reduce into different dQ tiles instead of contending for the same addresses
+                const int qi = (i + (int)blockIdx.x) % nq;
+                tma_load_2d(smem_u32(sQD + stage * 2 * AT_TILE), &tmQKV, fb, colQ, row_base + qi * AT_TQ);
+                tma_load_2d(smem_u32(sQD + stage * 2 * AT_TILE + AT_TILE), &tmDO, fb, colQ, row_base + qi * AT_TQ);
                 if (++stage == AB_QD_STAGES) {
                     stage = 0;
                     phase ^= 1;
@@ -695,8 +698,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         const float* lse = p.lse + ((long long)n * p.heads + h) * p.T;
         const float* delta = p.delta + ((long long)n * p.heads + h) * p.T;
         for (int i = 0; i < nq; ++i) {
-            const float l2 = lse[i * AT_TQ + r] * 1.4426950408889634f;
-            const float dl = delta[i * AT_TQ + r];
+            const int qi = (i + (int)blockIdx.x) % nq;     // same rotation as the TMA producer
+            const float l2 = lse[qi * AT_TQ + r] * 1.4426950408889634f;
+            const float dl = delta[qi * AT_TQ + r];
             mbar_wait(smem_u32(sdp_full), i & 1);
             tc_fence_after();
 #pragma unroll 1
@@ -735,7 +739,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             // dQ_i partial -> fp32 reduction
             mbar_wait(smem_u32(dq_full), i & 1);
             tc_fence_after();
-            float* dst = p.dq_acc + ((long long)row_base + i * AT_TQ + r) * p.C + h * AT_D;
+            float* dst = p.dq_acc + ((long long)row_base + qi * AT_TQ + r) * p.C + h * AT_D;
             {
                 // TMEM -> registers -> this thread's 128-byte half row of the fp32 staging tile -> one bulk
                 // reduce-add (TMA engine, fp32 atomics at L2) instead of 8 red.global.add.v4 instructions

@@ -339,7 +339,7 @@ template <int BN>
 struct WgradTcCfg {
     static constexpr int A_BYTES_ = 2 * WG_SUB;
     static constexpr int B_BYTES_ = (BN / 64) * WG_SUB;
-    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128) ? 6 : 8;
+    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192) ? 5 : (BN == 128) ? 6 : 8;
     static constexpr int ACC_STRIDE = (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
     static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
     static constexpr int SMEM = STAGES * (A_BYTES_ + B_BYTES_) + 1024 + 256;
@@ -617,10 +617,25 @@ static int wgrad_tc_launch_bn(const PuWgradArgs* a, cudaStream_t st) {
     p.ci_tiles = cdiv(a->C0 + a->C1, BN);
     p.taps = a->ksize * a->ksize;
     int base_items = p.co_tiles * p.ci_tiles * p.taps;
-    long long want = cdivll(2LL * num_sms(), base_items);
+    // split-K factor: items = base_items * splits are dealt round-robin to one CTA per SM, so pick the split count
+    // (up to ~4 waves) whose last wave is fullest -- 2*148/9 = 33 splits would leave a third wave with one item
     long long max_split = cdivll(p.px_blocks, 8);   // at least 8 K-blocks (512 pixels) per item
     if (max_split < 1) max_split = 1;
-    long long splits = want < 1 ? 1 : (want > max_split ? max_split : want);
+    const int sms = num_sms();
+    long long hi = cdivll(4LL * sms, base_items);
+    if (hi > max_split) hi = max_split;
+    if (hi < 1) hi = 1;
+    long long splits = 1;
+    double best = -1.0;
+    for (long long s = 1; s <= hi; ++s) {
+        const long long items = (long long)base_items * s;
+        const long long waves = cdivll(items, sms);
+        const double eff = (double)items / (double)(waves * sms);
+        if (eff > best + 1e-9) {      // ties: fewer splits (fewer partial-sum reductions)
+            best = eff;
+            splits = s;
+        }
+    }
     p.blocks_per_split = cdivll(p.px_blocks, splits);
     p.splits = (int)cdivll(p.px_blocks, p.blocks_per_split);
     p.total_items = base_items * p.splits;
@@ -650,6 +665,7 @@ static int wgrad_tc_launch_bn(const PuWgradArgs* a, cudaStream_t st) {
 int wgrad_tc_launch(const PuWgradArgs* a, cudaStream_t st) {
     int Ctot = a->C0 + a->C1;
     if (Ctot % 256 == 0) return wgrad_tc_launch_bn<256>(a, st);
+    if (Ctot % 192 == 0) return wgrad_tc_launch_bn<192>(a, st);
     if (Ctot % 128 == 0) return wgrad_tc_launch_bn<128>(a, st);
     return wgrad_tc_launch_bn<64>(a, st);
 }
