@@ -530,6 +530,231 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------
+// weight-gradient kernel with two accumulators per CTA.  The single-accumulator kernel above is bound by the
+// L2 -> shared-memory operand traffic (48 KB per 128x256x64 MMA block); sharing one operand between two
+// accumulators cuts it by 25-33 %:
+//   MODE 1: two Cout tiles (256 output channels) share the activation tile  (Cout % 256 == 0)
+//   MODE 2: two filter taps share the dy tile                                (3x3 layers with Cout == 128)
+// TMEM: accumulator 0 at column 0, accumulator 1 at column 256 (no double buffering: the K loops are hundreds of
+// blocks long, the epilogue is a negligible tail).
+// ------------------------------------------------------------------------------------------------
+template <int BN, int MODE>
+struct Wgrad2Cfg {
+    static constexpr int A_SUBS = (MODE == 1) ? 4 : 2;
+    static constexpr int B_SUBS = ((MODE == 1) ? 1 : 2) * (BN / 64);
+    static constexpr int STAGE_BYTES = (A_SUBS + B_SUBS) * WG_SUB;
+    static constexpr int MAX_STAGES = (227 * 1024 - 1280) / STAGE_BYTES;
+    static constexpr int STAGES = MAX_STAGES > 6 ? 6 : MAX_STAGES;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BN, int MODE>
+__global__ void __launch_bounds__(256, 1)
+wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX0,
+                 const __grid_constant__ CUtensorMap tmX1, const WgradTcParams p) {
+    using Cfg = Wgrad2Cfg<BN, MODE>;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
+    constexpr int A_BYTES2 = Cfg::A_SUBS * WG_SUB;
+    constexpr int B_ONE = (BN / 64) * WG_SUB;      // one activation (B) operand
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* tfull = bars + 2 * STAGES;
+    uint64_t* tempty = tfull + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmDY);
+        prefetch_tmap(&tmX0);
+        prefetch_tmap(&tmX1);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(smem_u32(&full[s]), 1);
+            mbar_init(smem_u32(&empty[s]), 1);
+        }
+        mbar_init(smem_u32(tfull), 1);
+        mbar_init(smem_u32(tempty), 4);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(smem_u32(tmem_slot), 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    const int Ctot = p.C0 + p.C1;
+    const int tap_groups = (MODE == 2) ? (p.taps + 1) / 2 : p.taps;
+    const int co_groups = (MODE == 1) ? (p.co_tiles + 1) / 2 : p.co_tiles;
+
+    // item -> (split, tap group, co group, ci tile)
+    auto decode = [&](int item, int& split, int& tg, int& cg, int& ci_t) {
+        ci_t = item % p.ci_tiles;
+        item /= p.ci_tiles;
+        cg = item % co_groups;
+        item /= co_groups;
+        tg = item % tap_groups;
+        split = item / tap_groups;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+                int split, tg, cg, ci_t;
+                decode(item, split, tg, cg, ci_t);
+                const int tap0 = (MODE == 2) ? 2 * tg : tg;
+                const int ntap = (MODE == 2 && tap0 + 1 < p.taps) ? 2 : 1;
+                const int co0 = (MODE == 1) ? cg * 256 : cg * 128;
+                long long b0 = (long long)split * p.blocks_per_split;
+                long long b1 = b0 + p.blocks_per_split;
+                if (b1 > p.px_blocks) b1 = p.px_blocks;
+                for (long long b = b0; b < b1; ++b) {
+                    const int bx = (int)(b % p.px_tiles_x);
+                    long long t = b / p.px_tiles_x;
+                    const int by = (int)(t % p.px_tiles_y);
+                    const int img = (int)(t / p.px_tiles_y);
+                    const int x0 = bx * WG_TW, y0 = by * WG_TH;
+                    mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+                    const uint32_t fb = smem_u32(&full[stage]);
+                    mbar_expect_tx(fb, A_BYTES2 + ntap * B_ONE + ((MODE == 1) ? 0 : 0));
+                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    uint8_t* sb = sa + A_BYTES2;
+#pragma unroll
+                    for (int j = 0; j < Cfg::A_SUBS; ++j)
+                        tma_load_4d(smem_u32(sa + j * WG_SUB), &tmDY, fb, co0 + j * 64, x0, y0, img);
+                    for (int tp = 0; tp < ntap; ++tp) {
+                        const int tap = tap0 + tp;
+                        const int dy = (p.ksize == 3) ? tap / 3 - 1 : 0;
+                        const int dx = (p.ksize == 3) ? tap % 3 - 1 : 0;
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j) {
+                            const int c = ci_t * BN + j * 64;
+                            uint8_t* dst = sb + tp * B_ONE + j * WG_SUB;
+                            if (c < p.C0)
+                                tma_load_4d(smem_u32(dst), &tmX0, fb, c, x0 + dx, y0 + dy, img);
+                            else
+                                tma_load_4d(smem_u32(dst), &tmX1, fb, c - p.C0, x0 + dx, y0 + dy, img);
+                        }
+                    }
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t IDESC = idesc_bf16_f32(128, BN, 1, 1);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t it = 0;
+            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+                int split, tg, cg, ci_t;
+                decode(item, split, tg, cg, ci_t);
+                const int ntap = (MODE == 2 && 2 * tg + 1 < p.taps) ? 2 : 1;
+                long long b0 = (long long)split * p.blocks_per_split;
+                long long b1 = b0 + p.blocks_per_split;
+                if (b1 > p.px_blocks) b1 = p.px_blocks;
+                mbar_wait(smem_u32(tempty), (it & 1) ^ 1);
+                tc_fence_after();
+                uint32_t first = 1;
+                for (long long b = b0; b < b1; ++b) {
+                    mbar_wait(smem_u32(&full[stage]), phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + A_BYTES2;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t acc_flag = (first && k == 0) ? 0u : 1u;
+                        if (MODE == 1) {
+                            const uint64_t bd = smem_desc_sw128(b_addr + k * 2048, WG_SUB, 1024);
+                            mma_f16_ss(tmem_base, smem_desc_sw128(a_addr + k * 2048, WG_SUB, 1024), bd, IDESC, acc_flag);
+                            mma_f16_ss(tmem_base + 256, smem_desc_sw128(a_addr + 2 * WG_SUB + k * 2048, WG_SUB, 1024), bd,
+                                       IDESC, acc_flag);
+                        } else {
+                            const uint64_t ad = smem_desc_sw128(a_addr + k * 2048, WG_SUB, 1024);
+                            mma_f16_ss(tmem_base, ad, smem_desc_sw128(b_addr + k * 2048, WG_SUB, 1024), IDESC, acc_flag);
+                            if (ntap == 2)
+                                mma_f16_ss(tmem_base + 256, ad, smem_desc_sw128(b_addr + B_ONE + k * 2048, WG_SUB, 1024),
+                                           IDESC, acc_flag);
+                        }
+                    }
+                    first = 0;
+                    mma_commit(smem_u32(&empty[stage]));
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                mma_commit(smem_u32(tfull));
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp - 4;
+        const long long row_stride = (long long)p.taps * Ctot;
+        uint32_t it = 0;
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+            int split, tg, cg, ci_t;
+            decode(item, split, tg, cg, ci_t);
+            const int tap0 = (MODE == 2) ? 2 * tg : tg;
+            const int ntap = (MODE == 2 && tap0 + 1 < p.taps) ? 2 : 1;
+            mbar_wait(smem_u32(tfull), it & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                int co, tap;
+                if (MODE == 1) {
+                    co = cg * 256 + half * 128 + q * 32 + lane;
+                    tap = tap0;
+                } else {
+                    if (half >= ntap) break;
+                    co = cg * 128 + q * 32 + lane;
+                    tap = tap0 + half;
+                }
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + half * 256;
+#pragma unroll 1
+                for (int c = 0; c < BN; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c, v);
+                    tc_wait_ld();
+                    if (co < p.Cout) {
+                        float* dst = p.dw + co * row_stride + (long long)tap * Ctot + ci_t * BN + c;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j),
+                                         "f"(__uint_as_float(v[j])), "f"(__uint_as_float(v[j + 1])),
+                                         "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                                         : "memory");
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(tempty));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 static bool tc_device_ok() {
@@ -605,9 +830,9 @@ bool wgrad_tc_applicable(const PuWgradArgs* a) {
     return true;
 }
 
-template <int BN>
+// MODE 0: single-accumulator kernel; MODE 1 / 2: wgrad_tc2_kernel (two Cout tiles / two taps per CTA)
+template <int BN, int MODE>
 static int wgrad_tc_launch_bn(const PuWgradArgs* a, cudaStream_t st) {
-    using Cfg = WgradTcCfg<BN>;
     WgradTcParams p;
     p.N = a->N; p.H = a->H; p.W = a->W; p.C0 = a->C0; p.C1 = a->C1; p.Cout = a->Cout; p.ksize = a->ksize;
     p.px_tiles_x = cdiv(a->W, WG_TW);
@@ -616,7 +841,9 @@ static int wgrad_tc_launch_bn(const PuWgradArgs* a, cudaStream_t st) {
     p.co_tiles = cdiv(a->Cout, 128);
     p.ci_tiles = cdiv(a->C0 + a->C1, BN);
     p.taps = a->ksize * a->ksize;
-    int base_items = p.co_tiles * p.ci_tiles * p.taps;
+    const int co_groups = (MODE == 1) ? (p.co_tiles + 1) / 2 : p.co_tiles;
+    const int tap_groups = (MODE == 2) ? (p.taps + 1) / 2 : p.taps;
+    int base_items = co_groups * p.ci_tiles * tap_groups;
     // split-K factor: items = base_items * splits are dealt round-robin to one CTA per SM, so pick the split count
     // (up to ~4 waves) whose last wave is fullest -- 2*148/9 = 33 splits would leave a third wave with one item
     long long max_split = cdivll(p.px_blocks, 8);   // at least 8 K-blocks (512 pixels) per item
@@ -653,21 +880,44 @@ static int wgrad_tc_launch_bn(const PuWgradArgs* a, cudaStream_t st) {
     if (rc) return rc;
 
     static bool attr_set = false;
-    if (!attr_set) {
-        PU_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-        attr_set = true;
-    }
     int grid = p.total_items < num_sms() ? p.total_items : num_sms();
-    wgrad_tc_kernel<BN><<<grid, 256, Cfg::SMEM, st>>>(tDY, tX0, tX1, p);
+    if constexpr (MODE == 0) {
+        using Cfg = WgradTcCfg<BN>;
+        if (!attr_set) {
+            PU_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+            attr_set = true;
+        }
+        wgrad_tc_kernel<BN><<<grid, 256, Cfg::SMEM, st>>>(tDY, tX0, tX1, p);
+    } else {
+        using Cfg = Wgrad2Cfg<BN, MODE>;
+        if (!attr_set) {
+            PU_CUDA(cudaFuncSetAttribute(wgrad_tc2_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM));
+            attr_set = true;
+        }
+        wgrad_tc2_kernel<BN, MODE><<<grid, 256, Cfg::SMEM, st>>>(tDY, tX0, tX1, p);
+    }
     return check_launch("wgrad_tc");
+}
+
+template <int BN>
+static int wgrad_tc_pick_mode(const PuWgradArgs* a, cudaStream_t st) {
+    static const int force = getenv("PU_WGRAD_MODE") ? atoi(getenv("PU_WGRAD_MODE")) : -1;   // experiments only
+    int mode = 0;
+    if (a->Cout % 256 == 0) mode = 1;                       // two Cout tiles share the activation tile
+    else if (a->ksize == 3) mode = 2;                       // two taps share the dy tile
+    if (force >= 0) mode = force;
+    if (mode == 1) return wgrad_tc_launch_bn<BN, 1>(a, st);
+    if (mode == 2 && a->ksize == 3) return wgrad_tc_launch_bn<BN, 2>(a, st);
+    return wgrad_tc_launch_bn<BN, 0>(a, st);
 }
 
 int wgrad_tc_launch(const PuWgradArgs* a, cudaStream_t st) {
     int Ctot = a->C0 + a->C1;
-    if (Ctot % 256 == 0) return wgrad_tc_launch_bn<256>(a, st);
-    if (Ctot % 192 == 0) return wgrad_tc_launch_bn<192>(a, st);
-    if (Ctot % 128 == 0) return wgrad_tc_launch_bn<128>(a, st);
-    return wgrad_tc_launch_bn<64>(a, st);
+    if (Ctot % 256 == 0) return wgrad_tc_pick_mode<256>(a, st);
+    if (Ctot % 192 == 0) return wgrad_tc_pick_mode<192>(a, st);
+    if (Ctot % 128 == 0) return wgrad_tc_pick_mode<128>(a, st);
+    return wgrad_tc_pick_mode<64>(a, st);
 }
 
 }  // namespace pu
