@@ -134,6 +134,8 @@ typedef struct PuGnBwdArgs {
     float* dbeta;         /* [C]                                                                       */
     float* dada;          /* [2C] or NULL                                                              */
     int acc_params;
+    float* colsum0;       /* optional [C0]: sum over (n, pixels) of the final dx0 values written (incl. dres  */
+    float* colsum1;       /* and the accumulated old value) = bias gradient of the conv that produced src0/1  */
 } PuGnBwdArgs;
 int pu_gn_bwd(const PuGnBwdArgs* a, void* stream);
 

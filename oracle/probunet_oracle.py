@@ -149,7 +149,7 @@ def unet_forward(sd: Dict[str, Tensor], x: Tensor, plan: dict, prefix: str = 'un
                  dropout_masks: Optional[Dict[str, Tensor]] = None, dropout_p: float = 0.10) -> Tensor:
     """networks.py:300-333 with label_dim=0, use_diffuse=False: emb = silu(zeros) = 0."""
     emb_dim = sd[prefix + 'map_layer1.weight'].shape[1]
-    emb = F.silu(torch.zeros(1, emb_dim, dtype=x.dtype))
+    emb = F.silu(torch.zeros(1, emb_dim, dtype=x.dtype, device=x.device))
     skips = []
     for spec in plan['enc']:
         p = f"{prefix}enc.{spec['name']}."

@@ -40,7 +40,8 @@ class PuGnArgs(C.Structure):
 class PuGnBwdArgs(C.Structure):
     _fields_ = [('f', PuGnArgs), ('dy', c_void_p), ('dres', c_void_p), ('dres_resample', c_int),
                 ('sums', c_void_p), ('dx0', c_void_p), ('dx1', c_void_p), ('acc0', c_int), ('acc1', c_int),
-                ('dgamma', c_void_p), ('dbeta', c_void_p), ('dada', c_void_p), ('acc_params', c_int)]
+                ('dgamma', c_void_p), ('dbeta', c_void_p), ('dada', c_void_p), ('acc_params', c_int),
+                ('colsum0', c_void_p), ('colsum1', c_void_p)]
 
 
 class PuFcombArgs(C.Structure):

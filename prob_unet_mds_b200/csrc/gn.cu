@@ -426,6 +426,10 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_reduce_kernel(PuGnBwdArg
 }
 
 template <typename T, bool FAST>
+__device__ __forceinline__ void gn_bwd_apply_rows(const PuGnBwdArgs& a, int rows, int n, int v, int pl, int PL,
+                                                  const double* smd, float (&cs)[8]);
+
+template <typename T, bool FAST>
 __global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_apply_kernel(PuGnBwdArgs a, int rows) {
     extern __shared__ double smd[];   // [G][2]: sum_c gamma' A, sum_c gamma' B
     const PuGnArgs& f = a.f;
@@ -433,7 +437,11 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_apply_kernel(PuGnBwdArgs
     const int n = blockIdx.y;
     const int PL = GN_THREADS / nvec;
     const int v = threadIdx.x % nvec, pl = threadIdx.x / nvec;
+    float* csm = reinterpret_cast<float*>(smd + 2 * f.G);   // [C] column sums of the written gradient (bias grads)
+    const bool want_cs = a.colsum0 != nullptr;
     for (int i = threadIdx.x; i < 2 * f.G; i += blockDim.x) smd[i] = 0.0;
+    if (want_cs)
+        for (int i = threadIdx.x; i < C; i += blockDim.x) csm[i] = 0.f;
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float gam = f.gamma[c];
@@ -443,7 +451,31 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_apply_kernel(PuGnBwdArgs
         atomicAdd(&smd[2 * g + 1], (double)gam * a.sums[((long long)n * C + c) * 2 + 1]);
     }
     __syncthreads();
-    if (pl >= PL) return;
+    float cs[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) cs[e] = 0.f;
+    if (pl < PL) gn_bwd_apply_rows<T, FAST>(a, rows, n, v, pl, PL, smd, cs);
+    if (want_cs) {
+        if (pl < PL) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) atomicAdd(&csm[v * 8 + e], cs[e]);
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            if (c < f.C0)
+                atomicAdd(a.colsum0 + c, csm[c]);
+            else if (a.colsum1)
+                atomicAdd(a.colsum1 + (c - f.C0), csm[c]);
+        }
+    }
+}
+
+// the per-thread pixel loop of gn_bwd_apply_kernel; cs accumulates the column sums of what is written
+template <typename T, bool FAST>
+__device__ __forceinline__ void gn_bwd_apply_rows(const PuGnBwdArgs& a, int rows, int n, int v, int pl, int PL,
+                                                  const double* smd, float (&cs)[8]) {
+    const PuGnArgs& f = a.f;
+    const int C = f.C0 + f.C1, Cg = C / f.G;
     const int c0 = v * 8;
     ChanConst k;
     gn_load_consts(f, n, c0, k);
@@ -515,6 +547,8 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_apply_kernel(PuGnBwdArgs
 #pragma unroll
                     for (int e = 0; e < 8; ++e) o[e] += old[e];
                 }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) cs[e] += o[e];
                 st8(dst + (long long)rr * stride, o);
             }
         }
@@ -538,6 +572,8 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_apply_kernel(PuGnBwdArgs
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] += old[e];
         }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) cs[e] += o[e];
         st8(p, o);
     }
 }
@@ -667,7 +703,9 @@ int pu_gn_bwd(const PuGnBwdArgs* a, void* stream) {
         if (rc) return rc;
     }
     {
-        const size_t smem = sizeof(double) * 2 * f.G;
+        if (a->colsum0) PU_CUDA(cudaMemsetAsync(a->colsum0, 0, sizeof(float) * f.C0, st));
+        if (a->colsum1 && f.C1 > 0) PU_CUDA(cudaMemsetAsync(a->colsum1, 0, sizeof(float) * f.C1, st));
+        const size_t smem = sizeof(double) * 2 * f.G + sizeof(float) * C;
         if (f.dtype == PU_F32)
             gn_bwd_apply_kernel<float, false><<<grid, GN_THREADS, smem, st>>>(*a, rows);
         else

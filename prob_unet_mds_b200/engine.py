@@ -25,6 +25,20 @@ def default_compute_dtype():
     raise ValueError(f'PROBUNET_B200_DTYPE={v!r}: expected bf16 or fp32')
 
 
+def input_nhwc(x, dtype, extra=None):
+    """fp32 NCHW model input (optionally followed channel-wise by `extra`, the posterior's target) -> NHWC in the
+    compute dtype.  In bf16 mode the channels are zero-padded to 64 so that the first convolutions (Cin = 3 / 6) and
+    their weight gradients run on the tcgen05 kernels instead of the CUDA-core ones (zero channels x zero-padded
+    weights contribute nothing)."""
+    N, Cx, H, W = x.shape
+    Ctot = Cx + (extra.shape[1] if extra is not None else 0)
+    pad = 64 if (dtype == torch.bfloat16 and H >= 8 and W >= 16) else Ctot
+    out = ops.nchw_to_nhwc(x.contiguous(), dtype, Cdst=max(pad, Ctot))
+    if extra is not None:
+        ops.nchw_to_nhwc(extra.contiguous(), dtype, out=out, c_off=Cx)
+    return out
+
+
 def _require_cuda(t, what):
     if not t.is_cuda:
         raise RuntimeError(f'probunet_b200: {what} must live on a CUDA device (there is no CPU path); got {t.device}')
@@ -58,8 +72,9 @@ class UNetEngine:
         self._step = 0
 
     # ---- packed parameters ------------------------------------------------------------------------------------------
-    def w_fwd(self, p, perm=None):
-        return self.cache.get((id(p), 'f', self.dtype), p, lambda: ops.pack_weight(p.detach(), 0, self.dtype, perm=perm))
+    def w_fwd(self, p, perm=None, Ci_pad=None):
+        return self.cache.get((id(p), 'f', self.dtype, Ci_pad), p,
+                              lambda: ops.pack_weight(p.detach(), 0, self.dtype, perm=perm, Ci_pad=Ci_pad))
 
     def w_dgrad(self, p, perm=None):
         return self.cache.get((id(p), 'd', self.dtype), p, lambda: ops.pack_weight(p.detach(), 1, self.dtype, perm=perm))
@@ -92,7 +107,9 @@ class UNetEngine:
                 bi += 1
             else:
                 xin = x
-                x = ops.conv2d(xin, self.w_fwd(mod.weight), mod.out_channels, mod.kernel, bias=mod.bias)
+                # xin may carry zero channels up to a multiple of 64 (input_nhwc) so that the tcgen05 kernel applies
+                x = ops.conv2d(xin, self.w_fwd(mod.weight, Ci_pad=xin.shape[3]), mod.out_channels, mod.kernel,
+                               bias=mod.bias)
                 rec = dict(kind='conv', mod=mod, xin=xin, out=x)
             if save:
                 tape.append(rec)
@@ -166,6 +183,8 @@ class UNetEngine:
         """dfeat: NHWC gradient wrt the features.  Fills grads[id(param)] for every live parameter."""
         u = self.unet
         gbuf = {}   # id(activation tensor) -> gradient tensor accumulated so far
+        self._gsum = {}   # id(gradient tensor) -> its per-channel sums (= bias gradient of the producing conv),
+                          # emitted by the gn_bwd call that wrote the tensor last
 
         rec = tape[-1]
         self._wgrad(grads, u.out_conv.weight, rec['h'], dfeat, 3)
@@ -173,18 +192,20 @@ class UNetEngine:
         dh = ops.conv2d(dfeat, self.w_dgrad(u.out_conv.weight), rec['h'].shape[3], 3)
         dg = torch.empty_like(u.out_norm.weight)
         db = torch.empty_like(u.out_norm.bias)
+        cs = torch.empty(rec['x'].shape[3], dtype=torch.float32, device=dh.device)
         dx, _ = ops.gn_bwd(rec['x'], rec['st'], u.out_norm.weight, u.out_norm.bias, dh, dg, db, silu=True,
-                           eps=u.out_norm.eps)
+                           eps=u.out_norm.eps, colsum0=cs)
         grads[id(u.out_norm.weight)] = dg
         grads[id(u.out_norm.bias)] = db
         gbuf[id(rec['x'])] = dx
+        self._gsum[id(dx)] = cs
 
         for rec in reversed(tape[:-1]):
             dout = gbuf.pop(id(rec['out']))
             if rec['kind'] == 'conv':
                 mod = rec['mod']
                 self._wgrad(grads, mod.weight, rec['xin'], dout, mod.kernel)
-                grads[id(mod.bias)] = ops.bias_grad(dout)
+                grads[id(mod.bias)] = self._colsum(dout)
                 continue
             self._block_bwd(rec, dout, grads, gbuf)
         return grads
@@ -198,7 +219,7 @@ class UNetEngine:
             heads = blk.num_heads
             perm = rec['perm']
             self._wgrad(grads, blk.proj.weight, rec['att'], dz, 1)
-            grads[id(blk.proj.bias)] = ops.bias_grad(dz)
+            grads[id(blk.proj.bias)] = self._colsum(dz)
             datt = ops.conv2d(dz, self.w_dgrad(blk.proj.weight), Cout, 1)
             dqkv = ops.attention_bwd(rec['qkv'], rec['att'], datt, rec['lse'], heads)
             self._wgrad(grads, blk.qkv.weight, rec['h2'], dqkv, 1, perm=perm)
@@ -209,33 +230,37 @@ class UNetEngine:
             dh2 = ops.conv2d(dqkv, self.w_dgrad(blk.qkv.weight, perm), Cout, 1)
             dg = torch.empty_like(blk.norm2.weight)
             db = torch.empty_like(blk.norm2.bias)
+            cs = torch.empty(Cout, dtype=torch.float32, device=dz.device)
             dy, _ = ops.gn_bwd(rec['y'], rec['st2'], blk.norm2.weight, blk.norm2.bias, dh2, dg, db, silu=False,
-                               eps=blk.norm2.eps, dres=dz)
+                               eps=blk.norm2.eps, dres=dz, colsum0=cs)
+            self._gsum[id(dy)] = cs
             grads[id(blk.norm2.weight)] = dg
             grads[id(blk.norm2.bias)] = db
         else:
             dy = dz
         # conv1
         self._wgrad(grads, blk.conv1.weight, rec['h1'], dy, 3)
-        grads[id(blk.conv1.bias)] = ops.bias_grad(dy)
+        bias_dy = self._colsum(dy)
+        grads[id(blk.conv1.bias)] = bias_dy
         dh1 = ops.conv2d(dy, self.w_dgrad(blk.conv1.weight), Cout, 3)
         dg = torch.empty_like(blk.norm1.weight)
         db = torch.empty_like(blk.norm1.bias)
         dada = torch.empty_like(blk.affine.bias)
+        cs = torch.empty(Cout, dtype=torch.float32, device=dy.device)
         da, _ = ops.gn_bwd(rec['a'], rec['st1'], blk.norm1.weight, blk.norm1.bias, dh1, dg, db, ada=blk.affine.bias,
-                           dada=dada, silu=True, dropout_p=rec['p'], seed=rec['seed'], eps=blk.norm1.eps)
+                           dada=dada, silu=True, dropout_p=rec['p'], seed=rec['seed'], eps=blk.norm1.eps, colsum0=cs)
         grads[id(blk.norm1.weight)] = dg
         grads[id(blk.norm1.bias)] = db
         grads[id(blk.affine.bias)] = dada
         # conv0
         self._wgrad(grads, blk.conv0.weight, rec['h0'], da, 3)
-        grads[id(blk.conv0.bias)] = ops.bias_grad(da)
+        grads[id(blk.conv0.bias)] = cs
         dh0 = ops.conv2d(da, self.w_dgrad(blk.conv0.weight), Cin, 3)
         # skip branch
         rs = rec['rs']
         if blk.skip is not None and blk.skip.weight is not None:
             self._wgrad(grads, blk.skip.weight, xa, dy, 1, src1=xb)
-            grads[id(blk.skip.bias)] = ops.bias_grad(dy)
+            grads[id(blk.skip.bias)] = bias_dy.clone()   # same values as conv1.bias' gradient, own storage
             dres = ops.conv2d(dy, self.w_dgrad(blk.skip.weight), Cin, 1)
             dres_rs = L.RS_NONE
         else:
@@ -245,14 +270,23 @@ class UNetEngine:
         db = torch.empty_like(blk.norm0.bias)
         ga = gbuf.get(id(xa))
         gb = gbuf.get(id(xb)) if xb is not None else None
+        csa = torch.empty(xa.shape[3], dtype=torch.float32, device=dy.device)
+        csb = torch.empty(xb.shape[3], dtype=torch.float32, device=dy.device) if xb is not None else None
         dxa, dxb = ops.gn_bwd(xa, rec['st0'], blk.norm0.weight, blk.norm0.bias, dh0, dg, db, src1=xb, silu=True,
                               resample=rs, eps=blk.norm0.eps, dres=dres, dres_resample=dres_rs,
-                              dx0=ga, dx1=gb, acc0=ga is not None, acc1=gb is not None)
+                              dx0=ga, dx1=gb, acc0=ga is not None, acc1=gb is not None, colsum0=csa, colsum1=csb)
         grads[id(blk.norm0.weight)] = dg
         grads[id(blk.norm0.bias)] = db
         gbuf[id(xa)] = dxa
+        self._gsum[id(dxa)] = csa
         if xb is not None:
             gbuf[id(xb)] = dxb
+            self._gsum[id(dxb)] = csb
+
+    def _colsum(self, g):
+        """Per-channel sum of a gradient tensor: taken from the gn_bwd call that wrote it, else computed."""
+        cs = self._gsum.get(id(g))
+        return cs if cs is not None else ops.bias_grad(g)
 
 
 def new_grad_sink(model):
@@ -286,7 +320,7 @@ class _UNetFunction(torch.autograd.Function):
     def forward(ctx, unet, x, *params):
         eng = unet.engine()
         ctx.unet = unet
-        xs = ops.nchw_to_nhwc(x.contiguous(), eng.dtype)
+        xs = input_nhwc(x, eng.dtype)
         eng._step += 1
         feat, tape = eng.forward(xs, unet.training, True, seed_base=_seed_base(eng._step))
         ctx.tape = tape
@@ -319,7 +353,7 @@ def unet_apply(unet, x):
     if torch.is_grad_enabled() and any(p.requires_grad for p in params):
         return _UNetFunction.apply(unet, x, *params)
     eng = unet.engine()
-    xs = ops.nchw_to_nhwc(x.contiguous(), eng.dtype)
+    xs = input_nhwc(x, eng.dtype)
     eng._step += 1
     feat, _ = eng.forward(xs, unet.training, False, seed_base=_seed_base(eng._step))
     return ops.nhwc_to_nchw(feat)
@@ -334,8 +368,9 @@ class GaussianEngine:
         self.dtype = dtype
         self.cache = _PackCache()
 
-    def w_fwd(self, p):
-        return self.cache.get((id(p), 'f', self.dtype), p, lambda: ops.pack_weight(p.detach(), 0, self.dtype))
+    def w_fwd(self, p, Ci_pad=None):
+        return self.cache.get((id(p), 'f', self.dtype, Ci_pad), p,
+                              lambda: ops.pack_weight(p.detach(), 0, self.dtype, Ci_pad=Ci_pad))
 
     def w_dgrad(self, p):
         return self.cache.get((id(p), 'd', self.dtype), p, lambda: ops.pack_weight(p.detach(), 1, self.dtype))
@@ -349,7 +384,7 @@ class GaussianEngine:
         x = xin
         acts = []
         for i, c in enumerate(convs):
-            r = ops.conv2d(x, self.w_fwd(c.weight), c.out_channels, 3, bias=c.bias, relu=True)
+            r = ops.conv2d(x, self.w_fwd(c.weight, Ci_pad=x.shape[3]), c.out_channels, 3, bias=c.bias, relu=True)
             last = i == len(convs) - 1
             acts.append((x, r))
             if not last:

@@ -143,8 +143,9 @@ def gn_apply(src0, stats, gamma, beta, src1=None, ada=None, silu=True, resample=
 
 def gn_bwd(src0, stats, gamma, beta, dy, dgamma, dbeta, src1=None, ada=None, dada=None, silu=True,
            resample=L.RS_NONE, dropout_p=0.0, seed=0, eps=1e-5, dres=None, dres_resample=L.RS_NONE,
-           dx0=None, dx1=None, acc0=False, acc1=False, acc_params=False):
-    """Returns (dx0, dx1).  dgamma/dbeta/dada are written (or accumulated into when acc_params)."""
+           dx0=None, dx1=None, acc0=False, acc1=False, acc_params=False, colsum0=None, colsum1=None):
+    """Returns (dx0, dx1).  dgamma/dbeta/dada are written (or accumulated into when acc_params).
+    colsum0 / colsum1 (optional fp32 [C0] / [C1]) receive the per-channel sums of the final dx0 / dx1."""
     N, H, W, C0 = _nhwc(src0)
     C1 = src1.shape[3] if src1 is not None else 0
     if dx0 is None:
@@ -156,7 +157,7 @@ def gn_bwd(src0, stats, gamma, beta, dy, dgamma, dbeta, src1=None, ada=None, dad
     sums = torch.empty((N, C0 + C1, 2), dtype=torch.float64, device=src0.device)
     f = _gn_args(src0, src1, stats, gamma, beta, ada, silu, resample, dropout_p, seed, None, eps)
     a = L.PuGnBwdArgs(f, ptr(dy), ptr(dres), dres_resample, ptr(sums), ptr(dx0), ptr(dx1), int(acc0), int(acc1),
-                      ptr(dgamma), ptr(dbeta), ptr(dada), int(acc_params))
+                      ptr(dgamma), ptr(dbeta), ptr(dada), int(acc_params), ptr(colsum0), ptr(colsum1))
     check(lib().pu_gn_bwd(C.byref(a), stream_ptr()), 'gn_bwd')
     return dx0, dx1
 

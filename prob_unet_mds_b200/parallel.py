@@ -190,7 +190,8 @@ def ensemble_sharded(model, x, num_samples, eps=None, group=None):
     lo, hi = shard_range(B, rank, world)
     with torch.no_grad():
         xs = x[lo:hi].contiguous()
-        feat, _ = model.unet.engine().forward(ops.nchw_to_nhwc(xs, dt), False, False)
+        from . import engine
+        feat, _ = model.unet.engine().forward(engine.input_nhwc(xs, dt), False, False)
         mu, ls, _ = model.prior.engine(dt).forward(model.prior._input(xs, None, dt), save=False)
         if world > 1:
             per = (B + world - 1) // world

@@ -48,10 +48,11 @@ class AxisAlignedConvGaussian(nn.Module):
         return self._engine
 
     def _input(self, x, target, dtype):
-        xin = ops.nchw_to_nhwc(x.contiguous(), dtype, Cdst=self.input_channels)
-        if self.posterior and target is not None:
-            ops.nchw_to_nhwc(target.contiguous(), dtype, out=xin, c_off=x.shape[1])
-        return xin
+        if self.posterior:
+            if target is None:
+                raise ValueError('the posterior net needs the target (prob_unet.py:57-58)')
+            return engine.input_nhwc(x, dtype, extra=target)
+        return engine.input_nhwc(x, dtype)
 
     def forward(self, x, target=None, dtype=None):
         """Inference-only convenience (no autograd): returns Independent(Normal(mu, exp(log_sigma)), 1)."""
@@ -170,7 +171,7 @@ class ProbabilisticUNet(nn.Module):
         B = x.shape[0]
         ue = self.unet.engine()
         ue._step += 1
-        feat, _ = ue.forward(ops.nchw_to_nhwc(x.contiguous(), dt), self.unet.training, False,
+        feat, _ = ue.forward(engine.input_nhwc(x, dt), self.unet.training, False,
                              seed_base=engine._seed_base(ue._step))
         self._flag_for(x.device)
         if training and target is not None:
@@ -199,7 +200,7 @@ class ProbabilisticUNet(nn.Module):
         self.unet.compute_dtype = dt
         B = x.shape[0]
         ue = self.unet.engine()
-        feat, _ = ue.forward(ops.nchw_to_nhwc(x.contiguous(), dt), False, False)
+        feat, _ = ue.forward(engine.input_nhwc(x, dt), False, False)
         mu, ls, _ = self.prior.engine(dt).forward(self.prior._input(x, None, dt), save=False)
         return self.decode_ensemble(feat, mu, ls, num_samples, eps)
 
@@ -237,7 +238,7 @@ class _ElboFunction(torch.autograd.Function):
         ue._step += 1
         x = x.contiguous()
         target = target.contiguous()
-        feat, utape = ue.forward(ops.nchw_to_nhwc(x, dt), model.unet.training, True, seed_base=engine._seed_base(ue._step))
+        feat, utape = ue.forward(engine.input_nhwc(x, dt), model.unet.training, True, seed_base=engine._seed_base(ue._step))
         pe, qe = model.prior.engine(dt), model.posterior.engine(dt)
         mu_p, ls_p, ptape = pe.forward(model.prior._input(x, None, dt), save=True)
         mu_q, ls_q, qtape = qe.forward(model.posterior._input(x, target, dt), save=True)
