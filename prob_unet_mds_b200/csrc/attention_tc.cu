@@ -110,7 +110,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParam
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // whole warp, warp-uniform control flow; mma_f16_ss / mma_commit elect one lane internally
             constexpr uint32_t IDESC_S = idesc_bf16_f32(128, 128, 0, 0);
             constexpr uint32_t IDESC_O = idesc_bf16_f32(128, 64, 0, 1);
             mbar_wait(smem_u32(q_full), 0);
@@ -339,7 +339,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdPara
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // whole warp, warp-uniform control flow; mma_f16_ss / mma_commit elect one lane internally
             constexpr uint32_t IDESC_S = idesc_bf16_f32(128, 128, 0, 0);
             constexpr uint32_t IDESC_O = idesc_bf16_f32(128, 64, 0, 1);
             mbar_wait(smem_u32(q_full), 0);
@@ -628,7 +628,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // whole warp, warp-uniform control flow; mma_f16_ss / mma_commit elect one lane internally
             constexpr uint32_t IDESC_S = idesc_bf16_f32(128, 128, 0, 0);     // S, dP
             constexpr uint32_t IDESC_T = idesc_bf16_f32(128, 64, 1, 1);      // dV, dK (both operands MN-major)
             constexpr uint32_t IDESC_Q = idesc_bf16_f32(128, 64, 0, 1);      // dQ

@@ -212,7 +212,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // the whole warp runs the issue loop (warp-uniform operands stay in uniform registers; a lane-0 branch made
+            // ptxas emit an ELECT/R2UR waterfall per MMA); mma_f16_ss / mma_commit elect one lane internally
             constexpr uint32_t IDESC = idesc_bf16_f32(128, BN, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
@@ -442,7 +443,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // the whole warp runs the issue loop (warp-uniform operands stay in uniform registers; a lane-0 branch made
+            // ptxas emit an ELECT/R2UR waterfall per MMA); mma_f16_ss / mma_commit elect one lane internally
             constexpr uint32_t IDESC = idesc_bf16_f32(128, BN, 1, 1);
             int stage = 0;
             uint32_t phase = 0;
@@ -654,7 +656,8 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // the whole warp runs the issue loop (warp-uniform operands stay in uniform registers; a lane-0 branch made
+            // ptxas emit an ELECT/R2UR waterfall per MMA); mma_f16_ss / mma_commit elect one lane internally
             constexpr uint32_t IDESC = idesc_bf16_f32(128, BN, 1, 1);
             int stage = 0;
             uint32_t phase = 0;

@@ -174,10 +174,41 @@ class UNetEngine:
 
     # ---- backward ---------------------------------------------------------------------------------------------------
     def _wgrad(self, grads, param, src0, dy, k, src1=None, perm=None):
-        dwp = ops.conv2d_wgrad(src0, dy, k, src1=src1)
-        g = grads.alloc(param)          # a view into an all-reduce bucket under data parallelism
-        ops.unpack_wgrad(dwp, g, perm=perm)
-        grads[id(param)] = g            # "written": may trigger the bucket's all-reduce
+        """Weight gradient, off the critical path: the data-gradient chain (dgrad -> GroupNorm backward -> dgrad ...)
+        never needs it, so it is issued on a side stream where its tensor-core work overlaps the HBM-bound
+        GroupNorm kernels of the main stream.  backward() joins the streams before returning."""
+        side = self._side_stream()
+        if side is None:
+            dwp = ops.conv2d_wgrad(src0, dy, k, src1=src1)
+            g = grads.alloc(param)          # a view into an all-reduce bucket under data parallelism
+            ops.unpack_wgrad(dwp, g, perm=perm)
+            grads[id(param)] = g            # "written": may trigger the bucket's all-reduce
+            return
+        main = torch.cuda.current_stream()
+        side.wait_stream(main)              # dy (and src) have been produced on the main stream
+        with torch.cuda.stream(side):
+            dwp = ops.conv2d_wgrad(src0, dy, k, src1=src1)
+            g = grads.alloc(param)
+            ops.unpack_wgrad(dwp, g, perm=perm)
+            grads[id(param)] = g
+        for t in (src0, dy, src1):
+            if t is not None:
+                t.record_stream(side)       # the caching allocator must not recycle them before the side stream is done
+        self._side_used = True
+
+    def _side_stream(self):
+        # measured on B200 (batch 64): 154.0 -> 151.9 ms per step only -- a persistent wgrad CTA per SM leaves too
+        # little room for the GroupNorm blocks to co-run -- so the side stream is opt-in
+        if os.environ.get('PROBUNET_B200_WGRAD_STREAM', '0') != '1':
+            return None
+        if getattr(self, '_side', None) is None:
+            self._side = torch.cuda.Stream()
+        return self._side
+
+    def join_side_stream(self):
+        if getattr(self, '_side_used', False):
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._side_used = False
 
     def backward(self, tape, dfeat, grads):
         """dfeat: NHWC gradient wrt the features.  Fills grads[id(param)] for every live parameter."""
@@ -187,9 +218,11 @@ class UNetEngine:
                           # emitted by the gn_bwd call that wrote the tensor last
 
         rec = tape[-1]
-        self._wgrad(grads, u.out_conv.weight, rec['h'], dfeat, 3)
+        # order everywhere below: data gradient first, then the weight gradient (side stream, starts once the dgrad
+        # has finished) so that it runs under the GroupNorm-backward kernels that follow on the main stream
         grads[id(u.out_conv.bias)] = ops.bias_grad(dfeat)
         dh = ops.conv2d(dfeat, self.w_dgrad(u.out_conv.weight), rec['h'].shape[3], 3)
+        self._wgrad(grads, u.out_conv.weight, rec['h'], dfeat, 3)
         dg = torch.empty_like(u.out_norm.weight)
         db = torch.empty_like(u.out_norm.bias)
         cs = torch.empty(rec['x'].shape[3], dtype=torch.float32, device=dh.device)
@@ -208,6 +241,7 @@ class UNetEngine:
                 grads[id(mod.bias)] = self._colsum(dout)
                 continue
             self._block_bwd(rec, dout, grads, gbuf)
+        self.join_side_stream()
         return grads
 
     def _block_bwd(self, rec, dz, grads, gbuf):
@@ -218,16 +252,16 @@ class UNetEngine:
         if blk.num_heads:
             heads = blk.num_heads
             perm = rec['perm']
-            self._wgrad(grads, blk.proj.weight, rec['att'], dz, 1)
             grads[id(blk.proj.bias)] = self._colsum(dz)
             datt = ops.conv2d(dz, self.w_dgrad(blk.proj.weight), Cout, 1)
+            self._wgrad(grads, blk.proj.weight, rec['att'], dz, 1)
             dqkv = ops.attention_bwd(rec['qkv'], rec['att'], datt, rec['lse'], heads)
-            self._wgrad(grads, blk.qkv.weight, rec['h2'], dqkv, 1, perm=perm)
             dbq = ops.bias_grad(dqkv)
             gq = torch.empty_like(blk.qkv.bias)
             ops.scatter(dbq, perm, gq)
             grads[id(blk.qkv.bias)] = gq
             dh2 = ops.conv2d(dqkv, self.w_dgrad(blk.qkv.weight, perm), Cout, 1)
+            self._wgrad(grads, blk.qkv.weight, rec['h2'], dqkv, 1, perm=perm)
             dg = torch.empty_like(blk.norm2.weight)
             db = torch.empty_like(blk.norm2.bias)
             cs = torch.empty(Cout, dtype=torch.float32, device=dz.device)
@@ -239,10 +273,10 @@ class UNetEngine:
         else:
             dy = dz
         # conv1
-        self._wgrad(grads, blk.conv1.weight, rec['h1'], dy, 3)
         bias_dy = self._colsum(dy)
         grads[id(blk.conv1.bias)] = bias_dy
         dh1 = ops.conv2d(dy, self.w_dgrad(blk.conv1.weight), Cout, 3)
+        self._wgrad(grads, blk.conv1.weight, rec['h1'], dy, 3)
         dg = torch.empty_like(blk.norm1.weight)
         db = torch.empty_like(blk.norm1.bias)
         dada = torch.empty_like(blk.affine.bias)
@@ -253,19 +287,19 @@ class UNetEngine:
         grads[id(blk.norm1.bias)] = db
         grads[id(blk.affine.bias)] = dada
         # conv0
-        self._wgrad(grads, blk.conv0.weight, rec['h0'], da, 3)
         grads[id(blk.conv0.bias)] = cs
         dh0 = ops.conv2d(da, self.w_dgrad(blk.conv0.weight), Cin, 3)
         # skip branch
         rs = rec['rs']
         if blk.skip is not None and blk.skip.weight is not None:
-            self._wgrad(grads, blk.skip.weight, xa, dy, 1, src1=xb)
             grads[id(blk.skip.bias)] = bias_dy.clone()   # same values as conv1.bias' gradient, own storage
             dres = ops.conv2d(dy, self.w_dgrad(blk.skip.weight), Cin, 1)
             dres_rs = L.RS_NONE
+            self._wgrad(grads, blk.skip.weight, xa, dy, 1, src1=xb)
         else:
             dres = dy
             dres_rs = rs
+        self._wgrad(grads, blk.conv0.weight, rec['h0'], da, 3)
         dg = torch.empty_like(blk.norm0.weight)
         db = torch.empty_like(blk.norm0.bias)
         ga = gbuf.get(id(xa))
