@@ -20,6 +20,7 @@
 //
 // Replaces cuDNN behind F.conv2d / convolution_backward (networks.py:87, prob_unet.py:33).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -124,25 +125,34 @@ struct ConvTcParams {
 constexpr int TILE_W = 16, TILE_H = 8;      // 128 output pixels per CTA tile
 constexpr int A_BYTES = 128 * 128;          // 128 rows x 64 bf16
 
-template <int BN>
+// MT = number of 128-pixel accumulators per CTA tile.  MT = 2 (a 16x16-pixel tile, two TMA boxes sharing one weight
+// tile) is used for Cout tiles of <= 128 channels: those layers are bound by the L2 -> shared-memory operand traffic
+// (32 KB per 128x128x64 MMA block), and sharing B between two accumulators cuts it by a quarter per FLOP.
+template <int BN, int MT = 1>
 struct ConvTcCfg {
     static constexpr int B_BYTES = BN * 128;
-    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192) ? 5 : (BN == 128) ? 6 : 8;
-    static constexpr int ACC_STRIDE = (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
+    static constexpr int A_STAGE = MT * A_BYTES;
+    static constexpr int MAX_STAGES = (227 * 1024 - 1280) / (A_STAGE + B_BYTES);
+    static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
+    static constexpr int ACC1 = (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
+    static constexpr int ACC_STRIDE = MT * ACC1;          // one accumulator stage
     static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-    static constexpr int SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+    static_assert(TMEM_COLS <= 512, "two accumulator stages must fit the 512 TMEM columns");
+    static constexpr int SMEM = STAGES * (A_STAGE + B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(256, 1)
+template <int BN, int MT>
+__global__ void __launch_bounds__(384, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const ConvTcParams p) {
-    using Cfg = ConvTcCfg<BN>;
+    using Cfg = ConvTcCfg<BN, MT>;
     constexpr int STAGES = Cfg::STAGES;
+    constexpr int A_STAGE = Cfg::A_STAGE;
+    constexpr int TH = TILE_H * MT;              // tile height in pixels
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
-    uint8_t* sB = smem + STAGES * A_BYTES;
+    uint8_t* sB = smem + STAGES * A_STAGE;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_BYTES);
     uint64_t* full = bars;
     uint64_t* empty = bars + STAGES;
@@ -165,7 +175,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&tfull[s]), 1);
-            mbar_init(smem_u32(&tempty[s]), 4);
+            mbar_init(smem_u32(&tempty[s]), 8);   // eight epilogue warps
         }
         fence_barrier_init();
     }
@@ -189,7 +199,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 t /= p.tiles_x;
                 const int ty = t % p.tiles_y;
                 const int img = t / p.tiles_y;
-                const int x0 = tx * TILE_W, y0 = ty * TILE_H, n0 = n_tile * BN;
+                const int x0 = tx * TILE_W, y0 = ty * TH, n0 = n_tile * BN;
                 for (int kb = 0; kb < p.nkb; ++kb) {
                     const int tap = kb / p.cblks;
                     const int cb = kb - tap * p.cblks;
@@ -197,12 +207,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     const int dx = (p.ksize == 3) ? tap % 3 - 1 : 0;
                     mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
                     const uint32_t fb = smem_u32(&full[stage]);
-                    mbar_expect_tx(fb, A_BYTES + Cfg::B_BYTES);
-                    if (cb < p.cblk0)
-                        tma_load_4d(smem_u32(sA + stage * A_BYTES), &tmA0, fb, cb * 64, x0 + dx, y0 + dy, img);
-                    else
-                        tma_load_4d(smem_u32(sA + stage * A_BYTES), &tmA1, fb, (cb - p.cblk0) * 64, x0 + dx, y0 + dy,
-                                    img);
+                    mbar_expect_tx(fb, A_STAGE + Cfg::B_BYTES);
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) {
+                        const uint32_t dst = smem_u32(sA + stage * A_STAGE + m * A_BYTES);
+                        if (cb < p.cblk0)
+                            tma_load_4d(dst, &tmA0, fb, cb * 64, x0 + dx, y0 + m * TILE_H + dy, img);
+                        else
+                            tma_load_4d(dst, &tmA1, fb, (cb - p.cblk0) * 64, x0 + dx, y0 + m * TILE_H + dy, img);
+                    }
                     tma_load_2d(smem_u32(sB + stage * Cfg::B_BYTES), &tmB, fb, kb * 64, n0);
                     if (++stage == STAGES) {
                         stage = 0;
@@ -226,13 +239,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 for (int kb = 0; kb < p.nkb; ++kb) {
                     mbar_wait(smem_u32(&full[stage]), phase);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(sA + stage * A_BYTES);
+                    const uint32_t a_addr = smem_u32(sA + stage * A_STAGE);
                     const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const uint64_t ad = smem_desc_sw128(a_addr + k * 32, 16, 1024);
                         const uint64_t bd = smem_desc_sw128(b_addr + k * 32, 16, 1024);
-                        mma_f16_ss(d_tmem, ad, bd, IDESC, (kb | k) ? 1u : 0u);
+#pragma unroll
+                        for (int m = 0; m < MT; ++m) {
+                            const uint64_t ad = smem_desc_sw128(a_addr + m * A_BYTES + k * 32, 16, 1024);
+                            mma_f16_ss(d_tmem + m * Cfg::ACC1, ad, bd, IDESC, (kb | k) ? 1u : 0u);
+                        }
                     }
                     mma_commit(smem_u32(&empty[stage]));
                     if (++stage == STAGES) {
@@ -246,7 +262,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             }
         }
     } else if (warp >= 4) {
-        const int q = warp - 4;
+        // eight epilogue warps: warps 4-7 and 8-11 both cover TMEM lanes 32*(warp%4)..+31 and take alternate
+        // 32-column chunks, which doubles the drain rate of the small-K (1x1) layers whose epilogue is the bottleneck
+        const int q = warp & 3;
+        const int ehalf = (warp - 4) >> 2;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -258,17 +277,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const int img = t / p.tiles_y;
             const int n0 = n_tile * BN;
             const int r = q * 32 + lane;
-            const int py = ty * TILE_H + r / TILE_W;
-            const int px = tx * TILE_W + r % TILE_W;
-            const bool valid = (py < p.H) && (px < p.W);
-            const long long pix = ((long long)img * p.H + py) * p.W + px;
             const float* bias = p.bias ? (p.bias + (p.bias_per_sample ? (long long)img * p.Cout : 0) + n0) : nullptr;
 
             mbar_wait(smem_u32(&tfull[acc]), acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_STRIDE;
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
+            for (int mc = ehalf; mc < MT * (BN / 32); mc += 2) {
+                const int m = mc / (BN / 32);
+                const int c = (mc % (BN / 32)) * 32;
+                const int py = ty * TH + m * TILE_H + r / TILE_W;
+                const int px = tx * TILE_W + r % TILE_W;
+                const bool valid = (py < p.H) && (px < p.W);
+                const long long pix = ((long long)img * p.H + py) * p.W + px;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_STRIDE + m * Cfg::ACC1;
                 uint32_t v[32];
                 tmem_ld32(taddr + c, v);
                 tc_wait_ld();
@@ -775,16 +796,16 @@ bool conv_tc_applicable(const PuConvArgs* a) {
     return true;
 }
 
-template <int BN>
+template <int BN, int MT>
 static int conv_tc_launch_bn(const PuConvArgs* a, cudaStream_t st) {
-    using Cfg = ConvTcCfg<BN>;
+    using Cfg = ConvTcCfg<BN, MT>;
     ConvTcParams p;
     p.N = a->N; p.H = a->H; p.W = a->W; p.Cout = a->Cout; p.ksize = a->ksize;
     p.cblk0 = a->C0 / 64;
     p.cblks = (a->C0 + a->C1) / 64;
     p.nkb = a->ksize * a->ksize * p.cblks;
     p.tiles_x = cdiv(a->W, TILE_W);
-    p.tiles_y = cdiv(a->H, TILE_H);
+    p.tiles_y = cdiv(a->H, TILE_H * MT);
     p.n_tiles = a->Cout / BN;
     long long total = (long long)a->N * p.tiles_x * p.tiles_y * p.n_tiles;
     PU_REQUIRE(total < (1LL << 31), "conv_tc: too many tiles");
@@ -810,19 +831,21 @@ static int conv_tc_launch_bn(const PuConvArgs* a, cudaStream_t st) {
 
     static bool attr_set = false;
     if (!attr_set) {
-        PU_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        PU_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
         attr_set = true;
     }
     int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-    conv_tc_kernel<BN><<<grid, 256, Cfg::SMEM, st>>>(tA0, tA1, tB, p);
+    conv_tc_kernel<BN, MT><<<grid, 384, Cfg::SMEM, st>>>(tA0, tA1, tB, p);
     return check_launch("conv_tc");
 }
 
 int conv_tc_launch(const PuConvArgs* a, cudaStream_t st) {
-    if (a->Cout % 256 == 0) return conv_tc_launch_bn<256>(a, st);
-    if (a->Cout % 192 == 0) return conv_tc_launch_bn<192>(a, st);
-    if (a->Cout % 128 == 0) return conv_tc_launch_bn<128>(a, st);
-    return conv_tc_launch_bn<64>(a, st);
+    static const int mt_env = getenv("PU_CONV_MT") ? atoi(getenv("PU_CONV_MT")) : 0;   // experiments: 1 forces MT = 1
+    if (a->Cout % 256 == 0) return conv_tc_launch_bn<256, 1>(a, st);
+    if (a->Cout % 192 == 0) return conv_tc_launch_bn<192, 1>(a, st);
+    const bool two = a->H >= 2 * TILE_H && mt_env != 1;      // 16x16-pixel tiles need at least 16 rows
+    if (a->Cout % 128 == 0) return two ? conv_tc_launch_bn<128, 2>(a, st) : conv_tc_launch_bn<128, 1>(a, st);
+    return two ? conv_tc_launch_bn<64, 2>(a, st) : conv_tc_launch_bn<64, 1>(a, st);
 }
 
 bool wgrad_tc_applicable(const PuWgradArgs* a) {
