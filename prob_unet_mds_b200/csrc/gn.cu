@@ -611,10 +611,28 @@ __global__ void gn_bwd_params_kernel(PuGnBwdArgs a) {
 }
 
 // pixel rows per block: aim at ~8 blocks per SM over the whole launch, but at least `min_rows` rows of work
+// The grid is (chunks per sample, N) with 3 resident blocks per SM (launch bounds): choose the chunk count (up to ~3
+// waves) whose last wave is fullest -- e.g. N = 64: 13 chunks -> 832 blocks = 1.87 waves of 444 instead of
+// 18 chunks -> 1152 blocks = 2.6 waves.
 static int rows_per_block(int HW, int N, int min_rows) {
-    int target_blocks = (148 * 8) / (N > 0 ? N : 1);
-    if (target_blocks < 1) target_blocks = 1;
-    int rows = cdiv(HW, target_blocks);
+    const int per_wave = 148 * 3;
+    int max_chunks = cdiv(HW, min_rows);
+    if (max_chunks < 1) max_chunks = 1;
+    int hi = (3 * per_wave) / (N > 0 ? N : 1);
+    if (hi < 1) hi = 1;
+    if (hi > max_chunks) hi = max_chunks;
+    int best_c = 1;
+    double best = -1.0;
+    for (int c = 1; c <= hi; ++c) {
+        const long long blocks = (long long)c * N;
+        const long long waves = cdivll(blocks, per_wave);
+        const double eff = (double)blocks / (double)(waves * per_wave);
+        if (eff > best + 1e-9 || (eff > best - 0.02 && blocks <= 2 * per_wave)) {   // prefer more, smaller blocks
+            if (eff > best) best = eff;
+            best_c = c;
+        }
+    }
+    int rows = cdiv(HW, best_c);
     if (rows < min_rows) rows = min_rows;
     return rows;
 }
