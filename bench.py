@@ -107,7 +107,7 @@ def cpu_reference_steps(steps, warmup, sample_batch=2, threads=None):
         r = O.elbo(leaf, x, t, eps, dropout_masks=masks)
         r['total'].backward()
         opt.step()
-        float(r['total'])
+        r['total'].item()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)

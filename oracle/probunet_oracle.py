@@ -35,6 +35,40 @@ import torch.nn.functional as F
 Tensor = torch.Tensor
 
 
+class ReluProbe:
+    """Test hook for the three ReLU sites of the path (prob_unet.py:56 encoder, :112-116 Fcomb).
+
+    ReLU is not differentiable at 0 and a fp32 implementation may land on either side of it for a unit whose
+    pre-activation is within rounding noise of zero; both are valid sub-gradients.  With ``record`` set the probe
+    stores every pre-activation; with ``flips = {call_index: flat_indices}`` it evaluates the backward with the
+    mask of exactly those units inverted (the forward value moves by |pre-activation| <= the probe threshold).
+    """
+
+    def __init__(self, flips=None, record=False):
+        self.flips = flips or {}
+        self.record = [] if record else None
+        self.calls = 0
+
+
+RELU_PROBE: Optional[ReluProbe] = None
+
+
+def _relu(x: Tensor) -> Tensor:
+    probe = RELU_PROBE
+    if probe is None:
+        return F.relu(x)
+    idx = probe.calls
+    probe.calls += 1
+    if probe.record is not None:
+        probe.record.append(x.detach())
+    flip = probe.flips.get(idx)
+    if flip is None:
+        return F.relu(x)
+    mask = (x > 0).reshape(-1).clone()
+    mask[flip] = ~mask[flip]
+    return x * mask.reshape(x.shape).to(x.dtype)
+
+
 # --------------------------------------------------------------------------------------
 # network plan (restates the constructor loops of networks.py:258-298)
 # --------------------------------------------------------------------------------------
@@ -176,7 +210,7 @@ def gaussian_encoder(sd: Dict[str, Tensor], prefix: str, x: Tensor, target: Opti
     i = 0
     while f'{prefix}encoder.{i}.weight' in sd:
         x = F.conv2d(x, sd[f'{prefix}encoder.{i}.weight'], sd[f'{prefix}encoder.{i}.bias'], padding=1)
-        x = F.avg_pool2d(F.relu(x), 2)
+        x = F.avg_pool2d(_relu(x), 2)
         i += 3
     h = x.mean(dim=[2, 3], keepdim=True)
     mu = F.conv2d(h, sd[prefix + 'conv_mu.weight'], sd[prefix + 'conv_mu.bias'])
@@ -188,8 +222,8 @@ def fcomb(sd: Dict[str, Tensor], feat: Tensor, z: Tensor, prefix: str = 'fcomb.'
     """prob_unet.py:100-121: tile z over HxW, concat, three 1x1 convs with ReLU between."""
     zt = z[:, :, None, None].expand(-1, -1, feat.shape[2], feat.shape[3])
     h = torch.cat([feat, zt], dim=1)
-    h = F.relu(F.conv2d(h, sd[prefix + 'layers.0.weight'], sd[prefix + 'layers.0.bias']))
-    h = F.relu(F.conv2d(h, sd[prefix + 'layers.2.weight'], sd[prefix + 'layers.2.bias']))
+    h = _relu(F.conv2d(h, sd[prefix + 'layers.0.weight'], sd[prefix + 'layers.0.bias']))
+    h = _relu(F.conv2d(h, sd[prefix + 'layers.2.weight'], sd[prefix + 'layers.2.bias']))
     return F.conv2d(h, sd[prefix + 'layers.4.weight'], sd[prefix + 'layers.4.bias'])
 
 

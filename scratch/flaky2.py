@@ -36,7 +36,7 @@ for it in range(5):
         first = None
         for idx, ((n0, o0, s0), (n1, o1, s1)) in enumerate(zip(rec[0], rec[it])):
             d = max(((a - b).norm() / (a.norm() + 1e-30)).item() for a, b in zip(o0, o1)) if o0 else 0.0
-            if d > 1e-5:
+            if d > 0:
                 first = (idx, n0, s0, d); break
         print(it, 'first op whose output differs from iteration 0:', first, 'of', len(rec[0]))
 print('--- detail: iteration 0 vs last')

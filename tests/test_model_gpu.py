@@ -30,14 +30,65 @@ def _model(L, precision, seed=0):
     return m, sd
 
 
-def _oracle_grads(sd, x, t, eps, dt=torch.float64):
+def _oracle_grads(sd, x, t, eps, dt=torch.float64, flips=None, record=False):
     """Gradients from the oracle evaluated in fp64.  The reference's own fp32 CPU gradients carry up to 3.4e-3
     relative error on the high-resolution encoder tensors (measured against fp64), so fp64 is the yardstick for
-    the gradient comparison; losses and outputs are also checked against the fp32 golden fixtures."""
+    the gradient comparison; losses and outputs are also checked against the fp32 golden fixtures.
+    ``flips`` / ``record`` drive oracle.ReluProbe (sub-gradient selection at ReLU pre-activations ~ 0)."""
     leaf = {k: (v.to(dt).clone().requires_grad_(True) if 'resample_filter' not in k else v.to(dt)) for k, v in sd.items()}
-    r = O.elbo(leaf, x.to(dt), t.to(dt), eps.to(dt))
-    r['total'].backward()
+    probe = O.ReluProbe(flips, record) if (flips is not None or record) else None
+    O.RELU_PROBE = probe
+    try:
+        r = O.elbo(leaf, x.to(dt), t.to(dt), eps.to(dt))
+        r['total'].backward()
+    finally:
+        O.RELU_PROBE = None
+    r['relu_preacts'] = probe.record if probe is not None else None
     return r, {k: v.grad for k, v in leaf.items() if getattr(v, 'grad', None) is not None}
+
+
+def _grad_errs(named, ref_grads):
+    errs = []
+    for k, g_ref in ref_grads.items():
+        if g_ref.abs().max() == 0:
+            continue
+        errs.append((_rel(named[k].grad.cpu(), g_ref), k))
+    errs.sort(reverse=True)
+    return errs
+
+
+def _select_subgradient(named, sd, x, t, eps, ref, ref_grads, tau=1e-5, max_units=12):
+    """A ReLU unit whose fp64 pre-activation is within ``tau`` of zero may legitimately be taken on either side by an
+    fp32 implementation (rounding noise there is ~2e-6), and because one unit of Fcomb carries O(1e-3) of the
+    ill-conditioned high-resolution gradients such a choice is visible.  Find those units, measure the effect of
+    inverting each one in the fp64 oracle, pick the 0/1 combination that explains the GPU gradients best (least
+    squares, then rounding) and return the oracle gradients for that selection."""
+    cands = []
+    for ci, pre in enumerate(ref['relu_preacts']):
+        flat = pre.reshape(-1).abs()
+        for i in torch.nonzero(flat < tau).reshape(-1).tolist():
+            cands.append((flat[i].item(), ci, i))
+    cands.sort()
+    cands = cands[:max_units]
+    if not cands:
+        return ref_grads, []
+    keys = [k for k, g in ref_grads.items() if g.abs().max() > 0]
+    scale = {k: 1.0 / ref_grads[k].norm().item() for k in keys}
+    resid = torch.cat([(named[k].grad.cpu().double() - ref_grads[k]).reshape(-1) * scale[k] for k in keys])
+    cols = []
+    for _, ci, i in cands:
+        _, g1 = _oracle_grads(sd, x, t, eps, flips={ci: torch.tensor([i])})
+        cols.append(torch.cat([(g1[k] - ref_grads[k]).reshape(-1) * scale[k] for k in keys]))
+    A = torch.stack(cols, dim=1)
+    a = torch.linalg.lstsq(A, resid[:, None]).solution[:, 0]
+    chosen = [c for c, w in zip(cands, a.tolist()) if w > 0.5]
+    if not chosen:
+        return ref_grads, []
+    flips = {}
+    for _, ci, i in chosen:
+        flips.setdefault(ci, []).append(i)
+    _, g = _oracle_grads(sd, x, t, eps, flips={ci: torch.tensor(v) for ci, v in flips.items()})
+    return g, chosen
 
 
 def _rel(a, b):
@@ -55,7 +106,7 @@ def test_elbo_and_grads_match_oracle_32(precision):
     m.eps_override = eps
     total, recon, kl = m.elbo(x.to(DEV), t.to(DEV))
     total.backward()
-    ref, ref_grads = _oracle_grads(sd, x, t, eps)
+    ref, ref_grads = _oracle_grads(sd, x, t, eps, record=True)
     tol = 1e-5 if precision == 'fp32' else 1e-3
     print(f'[{precision}] total {total.item():.6f} vs {float(fx["total"]):.6f}; recon {recon.item():.6f} vs '
           f'{float(fx["recon"]):.6f}; kl {kl.item():.6f} vs {float(fx["kl"]):.6f}')
@@ -71,25 +122,30 @@ def test_elbo_and_grads_match_oracle_32(precision):
     q = m.posterior_latent_space.base_dist
     assert torch.equal(m.last_z, q.loc + eps.to(DEV) * q.scale)
     # every gradient tensor
-    worst = []
     named = dict(m.named_parameters())
     for k, g_ref in ref_grads.items():
-        g = named[k].grad
-        assert g is not None, k
+        assert named[k].grad is not None, k
         if g_ref.abs().max() == 0:
-            assert g.abs().max().item() == 0, k
-            continue
-        worst.append((_rel(g.cpu(), g_ref), k))
-    worst.sort(reverse=True)
+            assert named[k].grad.abs().max().item() == 0, k
+    worst = _grad_errs(named, ref_grads)
     median = worst[len(worst) // 2][0]
     print(f'[{precision}] grad rel errs: median {median:.3e}, worst:', worst[:5])
-    # fp32 mode lands ~2e-6 from fp64 on every tensor *unless* one of the ~400k ReLU pre-activations of Fcomb / the
-    # prior / posterior nets sits within rounding noise of zero and flips: a single flipped unit carries O(1%) of the
-    # sum-MSE gradient and moves the ill-conditioned high-resolution encoder gradients by ~3e-3 (observed run to run;
-    # the reference's own fp32 CPU gradients are 3.4e-3 from fp64 on the same tensors).  Hence: tight bound on the
-    # median, loose bound on the maximum.  bf16 (eps 4e-3) lands at ~8e-2 on those tensors.
-    assert median <= (2e-5 if precision == 'fp32' else 5e-2), (median, worst[:5])
-    assert worst[0][0] <= (2e-2 if precision == 'fp32' else 1.5e-1), worst[:5]
+    if precision == 'fp32':
+        # fp32 mode lands ~2e-6 from fp64 on every tensor, up to the choice of sub-gradient at ReLU units whose
+        # pre-activation is within rounding noise of zero (see _select_subgradient; run-to-run atomics noise of
+        # ~1e-7 is enough to move such a unit, so the choice is not even stable between two runs).
+        if median > 2e-5 or worst[0][0] > 1e-4:
+            sel_grads, chosen = _select_subgradient(named, sd, x, t, eps, ref, ref_grads)
+            worst = _grad_errs(named, sel_grads)
+            median = worst[len(worst) // 2][0]
+            print(f'[fp32] after sub-gradient selection at {len(chosen)} near-zero ReLU unit(s) {chosen}: median '
+                  f'{median:.3e}, worst:', worst[:5])
+        assert median <= 2e-5, (median, worst[:5])
+        assert worst[0][0] <= 1e-4, worst[:5]
+    else:
+        # bf16 (eps 4e-3) flips thousands of such units and lands at ~8e-2 on the ill-conditioned tensors
+        assert median <= 5e-2, (median, worst[:5])
+        assert worst[0][0] <= 1.5e-1, worst[:5]
     # the never-used mapping layers get no gradient, like the reference
     for k in ('unet.map_layer0.weight', 'unet.map_layer0.bias', 'unet.map_layer1.weight', 'unet.map_layer1.bias'):
         assert named[k].grad is None
