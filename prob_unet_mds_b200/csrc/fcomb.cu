@@ -3,13 +3,18 @@
 //   W0 . [feat ; z] + b0 = W0f . feat + (W0z . z + b0),
 // the second term is a per-(sample, member) bias and, for ensembles, W0f . feat is computed once per pixel and
 // reused by all S members (encode once, re-run only Fcomb per sample).
-// fp32 CUDA-core math; one thread per pixel, weights broadcast from shared memory.
+// fp32 CUDA-core math; one thread per pixel, weights broadcast from shared memory.  (bf16 ensembles with S >= 4 go
+// to the tensor-core kernel in fcomb_tc.cu.)
 #include "../../include/probunet_b200.h"
 #include "common.cuh"
 
 namespace pu {
 
 constexpr int FC = 64;   // unet_output_channels == num_filters[0]
+
+// fcomb_tc.cu: tcgen05 ensemble decode (bf16, S >= 4 members per input)
+bool fcomb_members_tc_applicable(const PuFcombArgs* a);
+int fcomb_members_tc_launch(const PuFcombArgs* a, cudaStream_t st);
 
 template <typename T>
 __global__ void __launch_bounds__(128) fcomb_fwd_kernel(PuFcombArgs a) {
@@ -161,6 +166,7 @@ int pu_fcomb_fwd(const PuFcombArgs* a, void* stream) {
     PU_REQUIRE(a->num_classes >= 1 && a->num_classes <= 3, "pu_fcomb_fwd: num_classes must be 1..3 (got %d)", a->num_classes);
     PU_REQUIRE(a->S == 1 || (!a->h1_out && !a->h2_out), "pu_fcomb_fwd: hidden activations can only be saved for S == 1");
     cudaStream_t st = (cudaStream_t)stream;
+    if (fcomb_members_tc_applicable(a)) return fcomb_members_tc_launch(a, st);
     dim3 grid(cdiv(a->HW, 128), a->N);
     if (a->dtype == PU_F32)
         fcomb_fwd_kernel<float><<<grid, 128, 0, st>>>(*a);

@@ -435,6 +435,40 @@ def test_fcomb_fwd(dtype, S):
             assert rel_err(nchw(h2), hh) < (1e-5 if dtype == 'f32' else 4e-3)
 
 
+@pytest.mark.parametrize('shape', [(2, 16, 16, 5, 3), (1, 32, 32, 130, 3), (2, 8, 16, 8, 2)])
+def test_fcomb_members_tc(shape, monkeypatch):
+    """bf16 ensembles with S >= 4 and HW % 128 == 0 run the tcgen05 kernel (fcomb_tc.cu): check it against the fp32
+    formula (bf16 rounding of the hidden activations and weights, fp32 accumulation) and the CUDA-core kernel."""
+    N, H, W, S, nc = shape
+    Lz = 16
+    feat = rnd(N, 64, H, W, seed=1).to(torch.bfloat16).float()
+    z = rnd(N, S, Lz, seed=2)
+    w0 = rnd(64, 64 + Lz, 1, 1, seed=3) / 8
+    b0 = rnd(64, seed=4) * 0.1
+    w1 = rnd(64, 64, 1, 1, seed=5) / 8
+    b1 = rnd(64, seed=6) * 0.1
+    w2 = rnd(nc, 64, 1, 1, seed=7) / 8
+    b2 = rnd(nc, seed=8) * 0.1
+    fb = nhwc(feat, torch.bfloat16)
+    from prob_unet_mds_b200 import _lib
+    n0 = int(_lib._raw_lib().pu_launch_count(0))
+    out, _, _ = ops.fcomb_fwd(fb, z, w0, b0, w1, b1, w2, b2, S=S)
+    assert int(_lib._raw_lib().pu_launch_count(0)) == n0 + 1
+    monkeypatch.setenv('PU_FCOMB_TC', '0')
+    out_cc, _, _ = ops.fcomb_fwd(fb, z, w0, b0, w1, b1, w2, b2, S=S)
+    monkeypatch.delenv('PU_FCOMB_TC')
+    assert out.shape == (N, S, nc, H, W)
+    worst = 0.0
+    for s in range(S):
+        zt = z[:, s, :, None, None].expand(-1, -1, H, W)
+        h = F.relu(F.conv2d(torch.cat([feat, zt], 1), w0, b0))
+        ref = F.conv2d(F.relu(F.conv2d(h, w1, b1)), w2, b2)
+        worst = max(worst, rel_err(out[:, s], ref))
+        assert rel_err(out_cc[:, s], ref) < 1e-5
+    print('fcomb tc worst rel err', worst)
+    assert worst < 6e-3
+
+
 def test_fcomb_z_bwd_and_rsample_bwd():
     N, Lz = 3, 6
     rmean = rnd(N, 64, seed=1)
