@@ -16,6 +16,7 @@
 #include "attn_internal.h"
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include <stdlib.h>
 
 namespace pu {
 using namespace ptx;
@@ -546,6 +547,9 @@ struct AttnBwdParams {
     __nv_bfloat16* dqkv;      // [N*T][3C]
 };
 
+__device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -795,6 +799,264 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// backward, pipelined variant.  Same math and TMEM map as attn_bwd_tc_kernel, but S / dP are produced as two
+// 64-key halves with their own barriers and P / dS live in two shared-memory buffers (tile parity), so the tensor
+// pipe always runs one unit ahead of the softmax warps:
+//   MMA warp, tile i :  [P/dS half 0 ready] dQ_i  = dS_h0 K_h0 ; S/dP half 0 of tile i+1
+//                       [P/dS half 1 ready] dQ_i += dS_h1 K_h1 ; dV += P^T dO ; dK += dS^T Q ; S/dP half 1 of tile i+1
+//   softmax warps    :  half 0 of tile i ; dQ_{i-1} -> fp32 reductions ; half 1 of tile i
+// The softmax warps never wait for an MMA that was not issued at least half a tile earlier.
+// ------------------------------------------------------------------------------------------------
+constexpr int AB2_SMEM = 2 * AT_TILE /*K,V*/ + 2 * 2 * AT_TILE /*Q,dO x2 stages*/ + 2 * 2 * AT_TILE /*P x2*/ +
+                         2 * 2 * AT_TILE /*dS x2*/ + 1024 + 256;
+
+__global__ void __launch_bounds__(384, 1)
+attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                    const AttnBwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sK = smem;
+    uint8_t* sV = sK + AT_TILE;
+    uint8_t* sQD = sV + AT_TILE;                           // stage s: Q at +s*2*TILE, dO at +s*2*TILE + TILE
+    uint8_t* sP = sQD + 2 * 2 * AT_TILE;                   // buffer b at +b*2*TILE: two 64-key blocks of [128 q][128 B]
+    uint8_t* sDS = sP + 2 * 2 * AT_TILE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + 2 * 2 * AT_TILE);
+    uint64_t* kv_full = bars;
+    uint64_t* qd_full = bars + 1;                          // [2]
+    uint64_t* qd_empty = qd_full + 2;                      // [2]
+    uint64_t* sdp_full = qd_empty + 2;                     // [2] per key half
+    uint64_t* pds_full = sdp_full + 2;                     // [2] per key half
+    uint64_t* pds_free = pds_full + 2;                     // [2] per P/dS buffer
+    uint64_t* dq_full = pds_free + 2;
+    uint64_t* dq_empty = dq_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_empty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nh = blockIdx.y, n = nh / p.heads, h = nh % p.heads;
+    const int k0 = blockIdx.x * AT_TK;
+    const int nq = p.T / AT_TQ;
+    const int row_base = n * p.T;
+    const int colQ = h * AT_D, colK = p.C + h * AT_D, colV = 2 * p.C + h * AT_D;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmQKV);
+        prefetch_tmap(&tmDO);
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(smem_u32(kv_full), 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&qd_full[s]), 1);
+            mbar_init(smem_u32(&qd_empty[s]), 1);
+            mbar_init(smem_u32(&sdp_full[s]), 1);
+            mbar_init(smem_u32(&pds_full[s]), 8);    // one arrive per softmax warp
+            mbar_init(smem_u32(&pds_free[s]), 1);
+        }
+        mbar_init(smem_u32(dq_full), 1);
+        mbar_init(smem_u32(dq_empty), 8);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(smem_u32(tmem_slot), 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320,
+                   tDQ = tmem_base + 384;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(smem_u32(kv_full), 2 * AT_TILE);
+            tma_load_2d(smem_u32(sK), &tmQKV, smem_u32(kv_full), colK, row_base + k0);
+            tma_load_2d(smem_u32(sV), &tmQKV, smem_u32(kv_full), colV, row_base + k0);
+            for (int i = 0; i < nq; ++i) {
+                const int stage = i & 1;
+                mbar_wait(smem_u32(&qd_empty[stage]), ((i >> 1) & 1) ^ 1);
+                const uint32_t fb = smem_u32(&qd_full[stage]);
+                mbar_expect_tx(fb, 2 * AT_TILE);
+                // q tiles are walked starting at this CTA's own key-tile index: concurrently running CTAs of one
+                // (sample, head) then reduce into different dQ tiles instead of contending for the same addresses
+                const int qi = (i + (int)blockIdx.x) % nq;
+                tma_load_2d(smem_u32(sQD + stage * 2 * AT_TILE), &tmQKV, fb, colQ, row_base + qi * AT_TQ);
+                tma_load_2d(smem_u32(sQD + stage * 2 * AT_TILE + AT_TILE), &tmDO, fb, colQ, row_base + qi * AT_TQ);
+            }
+        }
+    } else if (warp == 1) {
+        // whole warp, warp-uniform control flow; mma_f16_ss / mma_commit elect one lane internally
+        constexpr uint32_t IDESC_H = idesc_bf16_f32(128, 64, 0, 0);      // S, dP halves (64 keys)
+        constexpr uint32_t IDESC_T = idesc_bf16_f32(128, 64, 1, 1);      // dV, dK (both operands MN-major)
+        constexpr uint32_t IDESC_Q = idesc_bf16_f32(128, 64, 0, 1);      // dQ
+        const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+        mbar_wait(smem_u32(kv_full), 0);
+        auto issue_sdp = [&](int stage, int half) {
+            const uint32_t q_addr = smem_u32(sQD + stage * 2 * AT_TILE);
+            const uint32_t do_addr = q_addr + AT_TILE;
+            const uint32_t kh = k_addr + half * (AT_TILE / 2), vh = v_addr + half * (AT_TILE / 2);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                mma_f16_ss(tS + half * 64, smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                           smem_desc_sw128(kh + k * 32, 16, 1024), IDESC_H, k ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                mma_f16_ss(tDP + half * 64, smem_desc_sw128(do_addr + k * 32, 16, 1024),
+                           smem_desc_sw128(vh + k * 32, 16, 1024), IDESC_H, k ? 1u : 0u);
+            mma_commit(smem_u32(&sdp_full[half]));
+        };
+        mbar_wait(smem_u32(&qd_full[0]), 0);
+        tc_fence_after();
+        issue_sdp(0, 0);
+        issue_sdp(0, 1);
+        for (int i = 0; i < nq; ++i) {
+            const int stage = i & 1;
+            const uint32_t q_addr = smem_u32(sQD + stage * 2 * AT_TILE);
+            const uint32_t do_addr = q_addr + AT_TILE;
+            const uint32_t p_addr = smem_u32(sP + stage * 2 * AT_TILE), ds_addr = smem_u32(sDS + stage * 2 * AT_TILE);
+            // ---- key half 0 ----
+            mbar_wait(smem_u32(&pds_full[0]), i & 1);
+            if (i > 0) mbar_wait(smem_u32(dq_empty), (i - 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                mma_f16_ss(tDQ, smem_desc_sw128(ds_addr + k * 32, 16, 1024),
+                           smem_desc_sw128(k_addr + k * 2048, AT_TILE, 1024), IDESC_Q, k ? 1u : 0u);
+            if (i + 1 < nq) {
+                mbar_wait(smem_u32(&qd_full[stage ^ 1]), ((i + 1) >> 1) & 1);
+                tc_fence_after();
+                issue_sdp(stage ^ 1, 0);
+            }
+            // ---- key half 1 ----
+            mbar_wait(smem_u32(&pds_full[1]), i & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                mma_f16_ss(tDQ, smem_desc_sw128(ds_addr + AT_TILE + k * 32, 16, 1024),
+                           smem_desc_sw128(k_addr + (4 + k) * 2048, AT_TILE, 1024), IDESC_Q, 1u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)     // K = 128 query rows, 16 per step
+                mma_f16_ss(tDV, smem_desc_sw128(p_addr + k * 2048, AT_TILE, 1024),
+                           smem_desc_sw128(do_addr + k * 2048, AT_TILE, 1024), IDESC_T, (i | k) ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                mma_f16_ss(tDK, smem_desc_sw128(ds_addr + k * 2048, AT_TILE, 1024),
+                           smem_desc_sw128(q_addr + k * 2048, AT_TILE, 1024), IDESC_T, (i | k) ? 1u : 0u);
+            mma_commit(smem_u32(dq_full));
+            mma_commit(smem_u32(&qd_empty[stage]));
+            mma_commit(smem_u32(&pds_free[stage]));
+            if (i + 1 < nq) issue_sdp(stage ^ 1, 1);
+        }
+    } else if (warp >= 4) {
+        // eight softmax warps: warp quadrant q owns query rows (= TMEM lanes) [32q, 32q+32); within a 64-key half
+        // warpgroup wg handles key columns [32wg, 32wg+32) and, for dQ / dK / dV, feature columns [32wg, 32wg+32)
+        const int q = warp & 3;
+        const int wg = (warp - 4) >> 2;
+        const int r = q * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        const float sc = 0.125f * 1.4426950408889634f;
+        const float* lse = p.lse + ((long long)n * p.heads + h) * p.T;
+        const float* delta = p.delta + ((long long)n * p.heads + h) * p.T;
+        float l2 = 0.f, dl = 0.f;
+        auto unit = [&](int i, int half) {
+            const int b = i & 1;
+            mbar_wait(smem_u32(&sdp_full[half]), i & 1);
+            tc_fence_after();
+            const int c = half * 64 + wg * 32;
+            uint32_t sv[32], dv[32];
+            tmem_ld32(tS + lane_off + c, sv);
+            tmem_ld32(tDP + lane_off + c, dv);
+            // the MMAs of tile i-2 must have finished reading this P / dS buffer
+            if (half == 0) mbar_wait(smem_u32(&pds_free[b]), ((i >> 1) & 1) ^ 1);
+            tc_wait_ld();
+            uint8_t* pb = sP + b * 2 * AT_TILE + half * AT_TILE + r * 128;
+            uint8_t* db = sDS + b * 2 * AT_TILE + half * AT_TILE + r * 128;
+            const int chunk0 = wg * 4;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                uint4 pk, dk;
+                __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&pk);
+                __nv_bfloat162* hd = reinterpret_cast<__nv_bfloat162*>(&dk);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int i0 = g * 8 + 2 * e;
+                    const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i0]), sc, -l2));
+                    const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i0 + 1]), sc, -l2));
+                    const float d0 = p0 * (__uint_as_float(dv[i0]) - dl) * 0.125f;
+                    const float d1 = p1 * (__uint_as_float(dv[i0 + 1]) - dl) * 0.125f;
+                    hp[e] = __floats2bfloat162_rn(p0, p1);
+                    hd[e] = __floats2bfloat162_rn(d0, d1);
+                }
+                const int off = ((chunk0 + g) ^ (r & 7)) << 4;
+                *reinterpret_cast<uint4*>(pb + off) = pk;
+                *reinterpret_cast<uint4*>(db + off) = dk;
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&pds_full[half]));
+        };
+        // dQ partial of tile i: TMEM -> registers -> vectorised fp32 reductions at L2.  (Measured alternatives that did
+        // not help: bulk reductions by the TMA engine from a staging tile, fragment-layout loads so that each warp
+        // instruction covers full 32-byte sectors, spreading the reductions over the next unit.  The reductions cost
+        // ~1.4 ms of a 4.8 ms T=4096 call whichever way they are issued: L2 atomic throughput.)
+        auto dq_out = [&](int i) {
+            const int qi = (i + (int)blockIdx.x) % nq;
+            mbar_wait(smem_u32(dq_full), i & 1);
+            tc_fence_after();
+            const int c = wg * 32;
+            uint32_t v[32];
+            tmem_ld32(tDQ + lane_off + c, v);
+            tc_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(dq_empty));
+            float* dst = p.dq_acc + ((long long)row_base + qi * AT_TQ + r) * p.C + h * AT_D + c;
+#pragma unroll
+            for (int e = 0; e < 32; e += 4)
+                red_add_v4(dst + e, __uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]),
+                           __uint_as_float(v[e + 3]));
+        };
+        for (int i = 0; i < nq; ++i) {
+            const int qi = (i + (int)blockIdx.x) % nq;     // same rotation as the TMA producer
+            l2 = lse[qi * AT_TQ + r] * 1.4426950408889634f;
+            dl = delta[qi * AT_TQ + r];
+            unit(i, 0);
+            if (i > 0) dq_out(i - 1);
+            unit(i, 1);
+        }
+        dq_out(nq - 1);
+        // the last dq_full commit also covers the final dV / dK accumulation
+        __nv_bfloat16* kp = p.dqkv + ((long long)row_base + k0 + r) * 3 * p.C + colK;
+        __nv_bfloat16* vp = p.dqkv + ((long long)row_base + k0 + r) * 3 * p.C + colV;
+        {
+            const int c = wg * 32;
+            uint32_t a[32], b[32];
+            tmem_ld32(tDK + lane_off + c, a);
+            tmem_ld32(tDV + lane_off + c, b);
+            tc_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 32; e += 8) {
+                float ka[8], va[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    ka[u] = __uint_as_float(a[e + u]);
+                    va[u] = __uint_as_float(b[e + u]);
+                }
+                st8(kp + c + e, ka);
+                st8(vp + c + e, va);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 // dqkv[row][0:C] = bf16(dq_acc[row][:])
 __global__ void attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, long long rows,
                                        int C) {
@@ -830,7 +1092,17 @@ int attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const 
     p.lse = lse; p.delta = delta; p.dq_acc = dq_acc;
     p.dqkv = (__nv_bfloat16*)dqkv;
     dim3 grid(T / AT_TK, N * heads);
-    attn_bwd_tc_kernel<<<grid, 384, AB_SMEM, st>>>(tm, tmdo, p);
+    const char* ev = getenv("PU_ATTN_BWD");       // PU_ATTN_BWD=1 selects the unpipelined kernel (A/B measurements)
+    if (ev && ev[0] == '1') {
+        attn_bwd_tc_kernel<<<grid, 384, AB_SMEM, st>>>(tm, tmdo, p);
+    } else {
+        static bool attr2 = false;
+        if (!attr2) {
+            PU_CUDA(cudaFuncSetAttribute(attn_bwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB2_SMEM));
+            attr2 = true;
+        }
+        attn_bwd_tc2_kernel<<<grid, 384, AB2_SMEM, st>>>(tm, tmdo, p);
+    }
     rc = check_launch("attn_bwd_tc");
     if (rc) return rc;
     long long total = (long long)N * T * (C / 8);
