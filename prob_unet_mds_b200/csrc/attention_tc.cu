@@ -34,6 +34,18 @@ struct AttnFwdParams {
     float* lse;
 };
 
+// 2^x for x <= 0 on the FMA / integer pipes (no MUFU): round-to-nearest split x = n + f with |f| <= 0.5, cubic
+// minimax for 2^f (relative error ~1e-4, far below the bf16 rounding of P), exponent added through the bit pattern.
+// Used for a fraction of the softmax exponentials so that MUFU.EX2 (16/clk/SM) is not the only path.
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -120.f);
+    const float t = x + 12582912.f;                 // 1.5 * 2^23: integer part lands in the low mantissa bits
+    const float f = x - (t - 12582912.f);
+    float pz = fmaf(f, 0.0555041f, 0.2402265f);
+    pz = fmaf(pz, f, 0.6931472f);
+    pz = fmaf(pz, f, 1.0f);
+    return __int_as_float(__float_as_int(pz) + (__float_as_int(t) << 23));
+}
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -266,6 +278,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParam
 // works for the other tile.  TMEM: S0 | S1 (128 cols each) | O0 | O1 (64 cols each).  Used when T % 256 == 0.
 // ------------------------------------------------------------------------------------------------
 constexpr int A2_KV_STAGES = 3;
+#ifndef A2_POLY_EVERY
+#define A2_POLY_EVERY 4               // every 4th exponential of a row goes to the FMA pipe (ex2_poly)
+#endif
 constexpr int A2_SMEM = 2 * AT_TILE /*Q0,Q1*/ + A2_KV_STAGES * 2 * AT_TILE /*K,V*/ + 2 * 2 * AT_TILE /*P0,P1*/ + 1024 + 256;
 
 __global__ void __launch_bounds__(384, 1)
@@ -444,7 +459,8 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdPara
                 float pv[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    pv[i] = ex2_approx(fmaf(__uint_as_float(v[i]), sc, -m_new));
+                    const float x = fmaf(__uint_as_float(v[i]), sc, -m_new);
+                    pv[i] = (i % A2_POLY_EVERY == A2_POLY_EVERY - 1) ? ex2_poly(x) : ex2_approx(x);
                     rs += pv[i];
                 }
                 uint8_t* kb_base = pb + (c >> 6) * AT_TILE + r * 128;

@@ -13,15 +13,29 @@
 namespace pu {
 
 constexpr int GN_THREADS = 256;
+constexpr int GN_BWD_BLOCKS = 2;   // resident blocks per SM of the backward kernels (128 registers, no spills)
 
 template <bool FAST>
 __device__ __forceinline__ float sigmoid_t(float u) {
     return FAST ? __fdividef(1.f, 1.f + __expf(-u)) : 1.f / (1.f + expf(-u));
 }
 
+// Per-channel constants.  xhat = (x - mu) * rstd and u = xhat * gamma' + beta' are evaluated as single FMAs from x in
+// the bf16 kernels (FAST): xhat = x * rstd + nmr, u = x * ag + bg.  The fp32 kernels keep the subtract-first form,
+// which does not lose precision when |mean| >> std.
 struct ChanConst {
     float mu[8], rstd[8], gam[8], bet[8];
+    float nmr[8], ag[8], bg[8];        // -mu*rstd, rstd*gamma', beta' - mu*rstd*gamma'
 };
+
+template <bool FAST>
+__device__ __forceinline__ float gn_xhat(const ChanConst& k, int e, float x) {
+    return FAST ? fmaf(x, k.rstd[e], k.nmr[e]) : (x - k.mu[e]) * k.rstd[e];
+}
+template <bool FAST>
+__device__ __forceinline__ float gn_u(const ChanConst& k, int e, float x) {
+    return FAST ? fmaf(x, k.ag[e], k.bg[e]) : fmaf((x - k.mu[e]) * k.rstd[e], k.gam[e], k.bet[e]);
+}
 
 // per-thread constants of channels [c0, c0+8) of sample n
 __device__ __forceinline__ void gn_load_consts(const PuGnArgs& f, int n, int c0, ChanConst& k) {
@@ -54,6 +68,9 @@ __device__ __forceinline__ void gn_load_consts(const PuGnArgs& f, int n, int c0,
         k.rstd[e] = rstd;
         k.gam[e] = gam;
         k.bet[e] = bet;
+        k.nmr[e] = -mean * rstd;
+        k.ag[e] = rstd * gam;
+        k.bg[e] = fmaf(-mean * rstd, gam, bet);
     }
 }
 
@@ -125,15 +142,22 @@ gn_stats_kernel(const T* __restrict__ s0, const T* __restrict__ s1, int C0, int 
         const int c0 = v * 8;
         const T* base = (c0 < C0) ? (s0 + (long long)n * HW * C0 + c0) : (s1 + (long long)n * HW * C1 + (c0 - C0));
         const int stride = (c0 < C0) ? C0 : C1;
-        for (int r = r0 + pl; r < r1; r += GN_NB * PL) {
-            Raw8<T> raw[GN_NB];
+        constexpr int SNB = 4;     // rows per trip; the next trip's loads are issued before this trip's math
+        Raw8<T> raw[SNB];
 #pragma unroll
-            for (int j = 0; j < GN_NB; ++j) {
-                const int rr = r + j * PL;
-                if (rr < r1) raw[j] = ldraw(base + (long long)rr * stride);
+        for (int j = 0; j < SNB; ++j) {
+            const int rr = r0 + pl + j * PL;
+            if (rr < r1) raw[j] = ldraw(base + (long long)rr * stride);
+        }
+        for (int r = r0 + pl; r < r1; r += SNB * PL) {
+            Raw8<T> nxt[SNB];
+#pragma unroll
+            for (int j = 0; j < SNB; ++j) {
+                const int rr = r + (SNB + j) * PL;
+                if (rr < r1) nxt[j] = ldraw(base + (long long)rr * stride);
             }
 #pragma unroll
-            for (int j = 0; j < GN_NB; ++j) {
+            for (int j = 0; j < SNB; ++j) {
                 if (r + j * PL >= r1) break;
                 float x[8];
                 unpack(raw[j], x);
@@ -143,6 +167,8 @@ gn_stats_kernel(const T* __restrict__ s0, const T* __restrict__ s1, int C0, int 
                     q[e] = fmaf(x[e], x[e], q[e]);
                 }
             }
+#pragma unroll
+            for (int j = 0; j < SNB; ++j) raw[j] = nxt[j];
         }
         // combine channels of the same group before touching shared memory
         int g = c0 / Cg;
@@ -196,12 +222,19 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_apply_kernel(PuGnArgs f, int
             xp = reinterpret_cast<const T*>(f.src1) + in_base * f.C1 + (c0 - f.C0);
             stride = f.C1;
         }
+        // software pipeline: the loads of the next GN_NB pixels are in flight while the current ones are processed
+        Raw8<T> raw[GN_NB];
+#pragma unroll
+        for (int j = 0; j < GN_NB; ++j) {
+            const int rr = r0 + pl + j * PL;
+            if (rr < r1) raw[j] = ldraw(xp + (long long)rr * stride);
+        }
         for (int op = r0 + pl; op < r1; op += GN_NB * PL) {
-            Raw8<T> raw[GN_NB];
+            Raw8<T> nxt[GN_NB];
 #pragma unroll
             for (int j = 0; j < GN_NB; ++j) {
-                const int rr = op + j * PL;
-                if (rr < r1) raw[j] = ldraw(xp + (long long)rr * stride);
+                const int rr = op + (GN_NB + j) * PL;
+                if (rr < r1) nxt[j] = ldraw(xp + (long long)rr * stride);
             }
 #pragma unroll
             for (int j = 0; j < GN_NB; ++j) {
@@ -211,7 +244,7 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_apply_kernel(PuGnArgs f, int
                 unpack(raw[j], x);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const float u = fmaf((x[e] - k.mu[e]) * k.rstd[e], k.gam[e], k.bet[e]);
+                    const float u = gn_u<FAST>(k, e, x[e]);
                     o[e] = f.silu ? u * sigmoid_t<FAST>(u) : u;
                 }
                 if (f.dropout_p > 0.f) {
@@ -222,6 +255,8 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_apply_kernel(PuGnArgs f, int
                 }
                 st8(y + (long long)rr * C, o);
             }
+#pragma unroll
+            for (int j = 0; j < GN_NB; ++j) raw[j] = nxt[j];
         }
         return;
     }
@@ -232,7 +267,7 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_apply_kernel(PuGnArgs f, int
             gn_load_x8<T>(f, in_base + op, c0, x);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const float u = fmaf((x[e] - k.mu[e]) * k.rstd[e], k.gam[e], k.bet[e]);
+                const float u = gn_u<FAST>(k, e, x[e]);
                 o[e] = f.silu ? u * sigmoid_t<FAST>(u) : u;
             }
         } else if (f.resample == PU_RS_UP) {
@@ -241,7 +276,7 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_apply_kernel(PuGnArgs f, int
             gn_load_x8<T>(f, in_base + (long long)(oy >> 1) * f.W + (ox >> 1), c0, x);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const float u = fmaf((x[e] - k.mu[e]) * k.rstd[e], k.gam[e], k.bet[e]);
+                const float u = gn_u<FAST>(k, e, x[e]);
                 o[e] = f.silu ? u * sigmoid_t<FAST>(u) : u;
             }
         } else {
@@ -254,7 +289,7 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_apply_kernel(PuGnArgs f, int
                 gn_load_x8<T>(f, in_base + (long long)(oy * 2 + (t >> 1)) * f.W + ox * 2 + (t & 1), c0, x);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const float u = fmaf((x[e] - k.mu[e]) * k.rstd[e], k.gam[e], k.bet[e]);
+                    const float u = gn_u<FAST>(k, e, x[e]);
                     o[e] += f.silu ? u * sigmoid_t<FAST>(u) : u;
                 }
             }
@@ -328,19 +363,21 @@ __device__ __forceinline__ void gn_du8_calc(const PuGnArgs& f, const ChanConst& 
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        xh[e] = (x[e] - k.mu[e]) * k.rstd[e];
-        float gg = ((keep >> e) & 1u) ? g[e] * inv_keep : 0.f;
+        xh[e] = gn_xhat<FAST>(k, e, x[e]);
+        float gg = ((keep >> e) & 1u) ? g[e] : 0.f;
         if (f.silu) {
-            const float u = fmaf(xh[e], k.gam[e], k.bet[e]);
+            const float u = gn_u<FAST>(k, e, x[e]);
             const float s = sigmoid_t<FAST>(u);
-            gg *= s * (1.f + u * (1.f - s));
+            gg *= (s * inv_keep) * fmaf(u, 1.f - s, 1.f);
+        } else {
+            gg *= inv_keep;
         }
         du[e] = gg;
     }
 }
 
 template <typename T, bool FAST>
-__global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_reduce_kernel(PuGnBwdArgs a, int rows) {
+__global__ void __launch_bounds__(GN_THREADS, GN_BWD_BLOCKS) gn_bwd_reduce_kernel(PuGnBwdArgs a, int rows) {
     // [C][2] block partial sums: fp32 shared-memory atomics (native, fast) within the block, fp64 atomics across
     // blocks (these sums cancel heavily -- signed terms -- so the long cross-block accumulation is done in fp64).
     extern __shared__ float sm[];
@@ -375,14 +412,24 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_reduce_kernel(PuGnBwdArg
                 stride = f.C1;
             }
             const T* gp = dy + base * C + c0;
+            // software pipeline: the loads of the next GN_NB rows are in flight while the current ones are processed
+            Raw8<T> xr[GN_NB], gr[GN_NB];
+#pragma unroll
+            for (int j = 0; j < GN_NB; ++j) {
+                const int rr = r0 + pl + j * PL;
+                if (rr < r1) {
+                    xr[j] = ldraw(xp + (long long)rr * stride);
+                    gr[j] = ldraw(gp + (long long)rr * C);
+                }
+            }
             for (int r = r0 + pl; r < r1; r += GN_NB * PL) {
-                Raw8<T> xr[GN_NB], gr[GN_NB];
+                Raw8<T> xn[GN_NB], gn[GN_NB];
 #pragma unroll
                 for (int j = 0; j < GN_NB; ++j) {
-                    const int rr = r + j * PL;
+                    const int rr = r + (GN_NB + j) * PL;
                     if (rr < r1) {
-                        xr[j] = ldraw(xp + (long long)rr * stride);
-                        gr[j] = ldraw(gp + (long long)rr * C);
+                        xn[j] = ldraw(xp + (long long)rr * stride);
+                        gn[j] = ldraw(gp + (long long)rr * C);
                     }
                 }
 #pragma unroll
@@ -401,6 +448,11 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_reduce_kernel(PuGnBwdArg
                         A[e] += du[e];
                         B[e] = fmaf(du[e], xh[e], B[e]);
                     }
+                }
+#pragma unroll
+                for (int j = 0; j < GN_NB; ++j) {
+                    xr[j] = xn[j];
+                    gr[j] = gn[j];
                 }
             }
         } else {
@@ -430,7 +482,7 @@ __device__ __forceinline__ void gn_bwd_apply_rows(const PuGnBwdArgs& a, int rows
                                                   const double* smd, float (&cs)[8]);
 
 template <typename T, bool FAST>
-__global__ void __launch_bounds__(GN_THREADS, 3) gn_bwd_apply_kernel(PuGnBwdArgs a, int rows) {
+__global__ void __launch_bounds__(GN_THREADS, GN_BWD_BLOCKS) gn_bwd_apply_kernel(PuGnBwdArgs a, int rows) {
     extern __shared__ double smd[];   // [G][2]: sum_c gamma' A, sum_c gamma' B
     const PuGnArgs& f = a.f;
     const int C = f.C0 + f.C1, nvec = C / 8, Cg = C / f.G;
@@ -484,8 +536,9 @@ __device__ __forceinline__ void gn_bwd_apply_rows(const PuGnBwdArgs& a, int rows
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         const int g = (c0 + e) / Cg;
-        s1[e] = (float)(smd[2 * g] * inv_m);
-        s2[e] = (float)(smd[2 * g + 1] * inv_m);
+        // dx = rstd * (du * gamma' - mean_g(gamma' du) - xhat * mean_g(gamma' du xhat)) = du * ag + s1 + xhat * s2
+        s1[e] = -k.rstd[e] * (float)(smd[2 * g] * inv_m);
+        s2[e] = -k.rstd[e] * (float)(smd[2 * g + 1] * inv_m);
     }
     const int HW = f.H * f.W;
     const int r0 = blockIdx.x * rows;
@@ -511,18 +564,24 @@ __device__ __forceinline__ void gn_bwd_apply_rows(const PuGnBwdArgs& a, int rows
                                   : reinterpret_cast<const T*>(f.src1) + base * f.C1 + (c0 - f.C0);
         const T* gp = dy + base * C + c0;
         const T* rp = dres ? dres + base * C + c0 : nullptr;
-        for (int r = r0 + pl; r < r1; r += NB * PL) {
-            Raw8<T> xr[NB], gr[NB], rr_[NB], od[NB];
+        Raw8<T> xr[NB], gr[NB], rr_[NB], od[NB];
+        auto load_rows = [&](int r, Raw8<T> (&xx)[NB], Raw8<T> (&gg)[NB], Raw8<T> (&dd)[NB], Raw8<T> (&oo)[NB]) {
 #pragma unroll
             for (int j = 0; j < NB; ++j) {
                 const int rr = r + j * PL;
                 if (rr < r1) {
-                    xr[j] = ldraw(xp + (long long)rr * stride);
-                    gr[j] = ldraw(gp + (long long)rr * C);
-                    if (rp) rr_[j] = ldraw(rp + (long long)rr * C);
-                    if (acc) od[j] = ldraw(dst + (long long)rr * stride);
+                    xx[j] = ldraw(xp + (long long)rr * stride);
+                    gg[j] = ldraw(gp + (long long)rr * C);
+                    if (rp) dd[j] = ldraw(rp + (long long)rr * C);
+                    if (acc) oo[j] = ldraw(dst + (long long)rr * stride);
                 }
             }
+        };
+        load_rows(r0 + pl, xr, gr, rr_, od);
+        for (int r = r0 + pl; r < r1; r += NB * PL) {
+            // software pipeline: next rows' loads are in flight while the current ones are processed
+            Raw8<T> xn[NB], gn[NB], rn[NB], on[NB];
+            load_rows(r + NB * PL, xn, gn, rn, on);
 #pragma unroll
             for (int j = 0; j < NB; ++j) {
                 const int rr = r + j * PL;
@@ -532,8 +591,8 @@ __device__ __forceinline__ void gn_bwd_apply_rows(const PuGnBwdArgs& a, int rows
                 unpack(gr[j], du);      // the reduce pass left du in the dy buffer
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const float xh = (x[e] - k.mu[e]) * k.rstd[e];
-                    o[e] = k.rstd[e] * (du[e] * k.gam[e] - s1[e] - xh * s2[e]);
+                    const float xh = gn_xhat<FAST>(k, e, x[e]);
+                    o[e] = fmaf(xh, s2[e], fmaf(du[e], k.ag[e], s1[e]));
                 }
                 if (rp) {
                     float d[8];
@@ -551,6 +610,13 @@ __device__ __forceinline__ void gn_bwd_apply_rows(const PuGnBwdArgs& a, int rows
                 for (int e = 0; e < 8; ++e) cs[e] += o[e];
                 st8(dst + (long long)rr * stride, o);
             }
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                xr[j] = xn[j];
+                gr[j] = gn[j];
+                rr_[j] = rn[j];
+                od[j] = on[j];
+            }
         }
         return;
     }
@@ -558,7 +624,7 @@ __device__ __forceinline__ void gn_bwd_apply_rows(const PuGnBwdArgs& a, int rows
         float xh[8], du[8], o[8];
         gn_du8<T, FAST>(f, k, dy, n, r, c0, xh, du);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = k.rstd[e] * (du[e] * k.gam[e] - s1[e] - xh[e] * s2[e]);
+        for (int e = 0; e < 8; ++e) o[e] = fmaf(xh[e], s2[e], fmaf(du[e], k.ag[e], s1[e]));
         if (dres) {
             float d[8];
             gn_gather8<T>(dres, a.dres_resample, n, f.H, f.W, r, C, c0, d);
@@ -614,8 +680,8 @@ __global__ void gn_bwd_params_kernel(PuGnBwdArgs a) {
 // The grid is (chunks per sample, N) with 3 resident blocks per SM (launch bounds): choose the chunk count (up to ~3
 // waves) whose last wave is fullest -- e.g. N = 64: 13 chunks -> 832 blocks = 1.87 waves of 444 instead of
 // 18 chunks -> 1152 blocks = 2.6 waves.
-static int rows_per_block(int HW, int N, int min_rows) {
-    const int per_wave = 148 * 3;
+static int rows_per_block(int HW, int N, int min_rows, int blocks_per_sm = 3) {
+    const int per_wave = 148 * blocks_per_sm;
     int max_chunks = cdiv(HW, min_rows);
     if (max_chunks < 1) max_chunks = 1;
     int hi = (3 * per_wave) / (N > 0 ? N : 1);
@@ -709,7 +775,7 @@ int pu_gn_bwd(const PuGnBwdArgs* a, void* stream) {
     const int HW = f.H * f.W;
     PU_CUDA(cudaMemsetAsync(a->sums, 0, sizeof(double) * 2 * f.N * C, st));
     const int PL = GN_THREADS / (C / 8);
-    const int rows = rows_per_block(HW, f.N, PL * 8);
+    const int rows = rows_per_block(HW, f.N, PL * 8, GN_BWD_BLOCKS);
     dim3 grid(cdiv(HW, rows), f.N);
     {
         const size_t smem = sizeof(float) * 2 * C;
