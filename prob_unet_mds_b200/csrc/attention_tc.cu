@@ -255,11 +255,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParam
         const long long row = (long long)row_base + q0 + r;
         __nv_bfloat16* op = p.out + row * p.C + h * AT_D;
 #pragma unroll
-        for (int d = 0; d < AT_D; d += 8) {
-            float o8[8];
+        for (int d = 0; d < AT_D; d += 16) {
+            float o16[16];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o8[e] = acc[d + e] * inv;
-            st8(op + d, o8);
+            for (int e = 0; e < 16; ++e) o16[e] = acc[d + e] * inv;
+            st16(op + d, o16);
         }
         p.lse[((long long)n * p.heads + h) * p.T + q0 + r] = (m + log2f(l)) * 0.6931471805599453f;
     }
@@ -489,11 +489,11 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdPara
         const long long row = (long long)row_base + q0 + t * AT_TQ + r;
         __nv_bfloat16* op = p.out + row * p.C + h * AT_D;
 #pragma unroll
-        for (int d = 0; d < AT_D; d += 8) {
-            float o8[8];
+        for (int d = 0; d < AT_D; d += 16) {
+            float o16[16];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o8[e] = acc[d + e] * inv;
-            st8(op + d, o8);
+            for (int e = 0; e < 16; ++e) o16[e] = acc[d + e] * inv;
+            st16(op + d, o16);
         }
         p.lse[((long long)n * p.heads + h) * p.T + q0 + t * AT_TQ + r] = (m + log2f(l)) * 0.6931471805599453f;
     }
@@ -794,15 +794,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             tmem_ld32(tDV + lane_off + c, b);
             tc_wait_ld();
 #pragma unroll
-            for (int e = 0; e < 32; e += 8) {
-                float ka[8], va[8];
+            for (int e = 0; e < 32; e += 16) {
+                float ka[16], va[16];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < 16; ++u) {
                     ka[u] = __uint_as_float(a[e + u]);
                     va[u] = __uint_as_float(b[e + u]);
                 }
-                st8(kp + c + e, ka);
-                st8(vp + c + e, va);
+                st16(kp + c + e, ka);
+                st16(vp + c + e, va);
             }
         }
     }
@@ -1052,15 +1052,15 @@ attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             tmem_ld32(tDV + lane_off + c, b);
             tc_wait_ld();
 #pragma unroll
-            for (int e = 0; e < 32; e += 8) {
-                float ka[8], va[8];
+            for (int e = 0; e < 32; e += 16) {
+                float ka[16], va[16];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < 16; ++u) {
                     ka[u] = __uint_as_float(a[e + u]);
                     va[u] = __uint_as_float(b[e + u]);
                 }
-                st8(kp + c + e, ka);
-                st8(vp + c + e, va);
+                st16(kp + c + e, ka);
+                st16(vp + c + e, va);
             }
         }
     }

@@ -77,6 +77,32 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const float (&v)[8]) {
     *reinterpret_cast<uint4*>(p) = r;
 }
 
+// ---- 16-wide bf16 load/store with one 256-bit access (sm_100: LDG/STG.E.256): a lane touches a full 32-byte sector,
+// so the row-per-lane access patterns of the tensor-core epilogues stop producing half-sector writes ----
+__device__ __forceinline__ void ld16(const __nv_bfloat16* p, float (&v)[16]) {
+    uint32_t r[8];
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r[i]));
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+    }
+}
+__device__ __forceinline__ void st16(__nv_bfloat16* p, const float (&v)[16]) {
+    uint32_t r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        r[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+                 "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+
 // ReLU that propagates NaN like torch.relu (fmaxf would swallow it and hide invalid inputs from the validate flag)
 __device__ __forceinline__ float relu_f(float v) { return v < 0.f ? 0.f : v; }
 __device__ __forceinline__ float silu_f(float u) { return u / (1.0f + expf(-u)); }

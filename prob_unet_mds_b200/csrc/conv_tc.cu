@@ -304,11 +304,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     if (p.residual) {
                         const __nv_bfloat16* rp = p.residual + pix * p.Cout + n0 + c;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            float rv[8];
-                            ld8(rp + j, rv);
+                        for (int j = 0; j < 32; j += 16) {
+                            float rv[16];
+                            ld16(rp + j, rv);
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) f[j + e] += rv[e];
+                            for (int e = 0; e < 16; ++e) f[j + e] += rv[e];
                         }
                     }
                     if (p.relu) {
@@ -317,11 +317,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     }
                     __nv_bfloat16* op = p.out + pix * p.Cout + n0 + c;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        float ov[8];
+                    for (int j = 0; j < 32; j += 16) {
+                        float ov[16];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) ov[e] = f[j + e];
-                        st8(op + j, ov);
+                        for (int e = 0; e < 16; ++e) ov[e] = f[j + e];
+                        st16(op + j, ov);
                     }
                 }
             }
