@@ -90,6 +90,47 @@ __global__ void global_mean_kernel(const T* __restrict__ x, float* __restrict__ 
     m[(long long)n * C + c] = s / (float)HW;
 }
 
+// same, pixels split over blocks (grid (chunks, N), 256 threads = C/8 channel vectors x pixel lanes): per-thread partial
+// sums -> shared-memory atomics -> one global atomic per (block, channel).  m must be zeroed by the caller.
+template <typename T>
+__global__ void __launch_bounds__(256) global_mean_split_kernel(const T* __restrict__ x, float* __restrict__ m, int HW,
+                                                                 int C, int rows) {
+    extern __shared__ float gm_sm[];   // [C]
+    const int n = blockIdx.y;
+    const int nvec = C / 8, PL = 256 / nvec;
+    const int v = threadIdx.x % nvec, pl = threadIdx.x / nvec;
+    for (int i = threadIdx.x; i < C; i += 256) gm_sm[i] = 0.f;
+    __syncthreads();
+    const int r0 = blockIdx.x * rows;
+    int r1 = r0 + rows;
+    if (r1 > HW) r1 = HW;
+    if (pl < PL) {
+        float s[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s[e] = 0.f;
+        const T* base = x + (long long)n * HW * C + v * 8;
+        int r = r0 + pl;
+        for (; r + PL < r1; r += 2 * PL) {
+            float a[8], b[8];
+            ld8(base + (long long)r * C, a);
+            ld8(base + (long long)(r + PL) * C, b);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s[e] += a[e] + b[e];
+        }
+        if (r < r1) {
+            float a[8];
+            ld8(base + (long long)r * C, a);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s[e] += a[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(&gm_sm[v * 8 + e], s[e]);
+    }
+    __syncthreads();
+    const float inv = 1.f / (float)HW;
+    for (int i = threadIdx.x; i < C; i += 256) atomicAdd(m + (long long)n * C + i, gm_sm[i] * inv);
+}
+
 template <typename T>
 __global__ void relu_mean_bwd_kernel(const float* __restrict__ dm, const T* __restrict__ r, T* __restrict__ dr, int N,
                                      int HW, int C) {
@@ -273,6 +314,19 @@ int pu_relu_pool_bwd(const void* dp, const void* r, void* dr, int N, int H, int 
 int pu_global_mean(const void* x, float* m, int N, int HW, int C, int dtype, void* stream) {
     PU_REQUIRE(x && m && N > 0 && HW > 0 && C > 0, "pu_global_mean: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == PU_BF16 && C % 8 == 0 && C / 8 <= 256 && HW >= 1024) {
+        // large images (the Fcomb backward reduces 128x128 pixels): split the pixels over ~4 blocks per SM.  The fp32
+        // mode keeps the one-thread-per-channel kernel below: fixed summation order, bit-reproducible mu / log sigma.
+        PU_CUDA(cudaMemsetAsync(m, 0, sizeof(float) * (size_t)N * C, st));
+        int chunks = cdiv(148 * 4, N);
+        const int PL = 256 / (C / 8);
+        if (chunks > HW / (4 * PL)) chunks = HW / (4 * PL);
+        if (chunks < 1) chunks = 1;
+        const int rows = cdiv(HW, chunks);
+        dim3 g2(cdiv(HW, rows), N);
+        global_mean_split_kernel<__nv_bfloat16><<<g2, 256, sizeof(float) * C, st>>>((const __nv_bfloat16*)x, m, HW, C, rows);
+        return check_launch("global_mean");
+    }
     dim3 grid(cdiv(C, 128), N);
     if (dtype == PU_F32)
         global_mean_kernel<float><<<grid, 128, 0, st>>>((const float*)x, m, HW, C);

@@ -73,6 +73,28 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ src, float* __rest
     }
 }
 
+// 3x3 variant: one block per (128 input channels, output channel).  The nine [tap][ci] source rows are read with
+// coalesced loads into shared memory and written back as one contiguous run of 128*9 floats in [ci][tap] order
+// (the element-wise kernel above reads with a 9-way stride).
+__global__ void __launch_bounds__(128) unpack_wgrad3_kernel(const float* __restrict__ src, float* __restrict__ dst, int Ci,
+                                                            int Ci_pad, const int* __restrict__ perm, int accumulate,
+                                                            long long dst_co_stride) {
+    __shared__ float t[9][129];
+    const int co = blockIdx.y, ci0 = blockIdx.x * 128, tid = threadIdx.x;
+    const int nci = min(128, Ci - ci0);
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap)
+        t[tap][tid] = tid < nci ? src[((long long)co * 9 + tap) * Ci_pad + ci0 + tid] : 0.f;
+    __syncthreads();
+    const int dco = perm ? perm[co] : co;
+    float* d = dst + (long long)dco * dst_co_stride + (long long)ci0 * 9;
+    for (int j = tid; j < nci * 9; j += 128) {
+        const int ci = j / 9, tap = j - ci * 9;
+        const float v = t[tap][ci];
+        d[j] = accumulate ? d[j] + v : v;
+    }
+}
+
 __global__ void gather_kernel(const float* src, const int* perm, float* dst, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[perm[i]];
@@ -145,6 +167,11 @@ int pu_unpack_conv_wgrad(const float* src, float* dst, int Co, int Ci, int k, in
     cudaStream_t st = (cudaStream_t)stream;
     if (dst_co_stride <= 0) dst_co_stride = (long long)Ci * k * k;
     long long total = (long long)Co * Ci * k * k;
+    if (k == 3 && Co <= 65535) {
+        dim3 grid(pu::cdiv(Ci, 128), Co);
+        pu::unpack_wgrad3_kernel<<<grid, 128, 0, st>>>(src, dst, Ci, Ci_pad, out_perm, accumulate, dst_co_stride);
+        return pu::check_launch("unpack_conv_wgrad");
+    }
     pu::unpack_wgrad_kernel<<<pu::grid_for(total), 256, 0, st>>>(src, dst, Co, Ci, k, Ci_pad, out_perm, accumulate,
                                                                 dst_co_stride);
     return pu::check_launch("unpack_conv_wgrad");

@@ -75,6 +75,25 @@ def test_pack_unpack():
     assert torch.equal(g, 2 * w)
 
 
+def test_unpack_wgrad_3x3_blocked():
+    """Co x Ci large enough for several 128-channel blocks and a ragged tail (unpack_wgrad3_kernel)."""
+    w = rnd(12, 200, 3, 3, seed=5)
+    perm = torch.randperm(12).to(DEV).int()
+    pp = ops.pack_weight(w, 0, torch.float32, Ci_pad=256, perm=perm)
+    g = torch.zeros_like(w)
+    ops.unpack_wgrad(pp, g, perm=perm)
+    assert torch.equal(g, w)
+    ops.unpack_wgrad(pp, g, perm=perm, accumulate=True)
+    assert torch.equal(g, 2 * w)
+
+
+def test_global_mean_split():
+    """bf16 with >= 1024 pixels takes the pixel-split kernel (shared + global atomics)."""
+    x = rnd(3, 64, 40, 32, seed=6).to(torch.bfloat16).float()
+    m = ops.global_mean(nhwc(x, torch.bfloat16))
+    assert torch.allclose(m, x.mean(dim=(2, 3)), atol=2e-6, rtol=1e-5)
+
+
 CONV_CASES = [
     # N, H, W, C0, C1, Cout, k
     (2, 16, 16, 64, 0, 64, 3),
