@@ -15,9 +15,16 @@ namespace pu {
 constexpr int GN_THREADS = 256;
 constexpr int GN_BWD_BLOCKS = 2;   // resident blocks per SM of the backward kernels (128 registers, no spills)
 
+// FAST (bf16 kernels): sigmoid(u) = 0.5 tanh(u/2) + 0.5 with the single-MUFU tanh.approx (relative error ~2^-11, far
+// below bf16 rounding) instead of ex2 + rcp -- the GroupNorm kernels are bound by instruction issue, not by HBM.
 template <bool FAST>
 __device__ __forceinline__ float sigmoid_t(float u) {
-    return FAST ? __fdividef(1.f, 1.f + __expf(-u)) : 1.f / (1.f + expf(-u));
+    if (FAST) {
+        float t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * u));
+        return fmaf(t, 0.5f, 0.5f);
+    }
+    return 1.f / (1.f + expf(-u));
 }
 
 // Per-channel constants.  xhat = (x - mu) * rstd and u = xhat * gamma' + beta' are evaluated as single FMAs from x in
