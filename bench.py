@@ -137,6 +137,26 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def ncu_traffic():
+    """DRAM bytes (read + write) of the dominant kernel's headline launch from the committed `ncu --set full` capture
+    (profiles/r1_ncu_heavy_kernels.tsv, first conv_tc_kernel row: 256->256 3x3 at 128x128, batch 64)."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'r1_ncu_heavy_kernels.tsv')
+    try:
+        rows = [l.rstrip('\n').split('\t') for l in open(path)]
+        hdr = rows[0]
+        for r in rows[1:]:
+            if r[0].startswith('conv_tc_kernel<256, 1>'):
+                rd, wr = float(r[hdr.index('dram_rd_MB')]), float(r[hdr.index('dram_wr_MB')])
+                alg = 2 * 64 * 128 * 128 * 256 * 2 / 1e6
+                return {'traffic': (rd + wr) * 1e6,
+                        'traffic_note': f'ncu dram read+write of one conv_tc_kernel<256,1> launch (256->256 3x3, 128x128, '
+                                        f'batch 64): {rd + wr:.0f} MB vs {alg:.0f} MB algorithmic (input + output once); '
+                                        'source profiles/r1_ncu_heavy_kernels.tsv'}
+    except (OSError, ValueError, IndexError):
+        pass
+    return {}
+
+
 def workload_config(n_gpus, per_gpu_batch, note=None):
     c = {'workload': 'ProbabilisticUNet ELBO training step (zero_grad, elbo fwd, backward, AdamW), 3x128x128 tiles, '
                      f'latent_dim {LATENT}, num_filters [64,128,256,512] (BASELINE.json configs[1])',
@@ -225,10 +245,29 @@ def run_ours(args):
     barrier()
     ms_e2e = s_evt.elapsed_time(e_evt) / args.steps
 
+    # ---- secondary metric: ensemble member-samples/s.  U-Net + prior once per input, then the
+    # fused Fcomb decode for 100 latent samples; inputs sharded over ranks (no communication), outputs stay on device.
+    ms_ens = None
+    if args.ensemble_members > 0:
+        model.eval()
+        with torch.no_grad():
+            for _ in range(2):
+                model.sample_ensemble(x_dev, args.ensemble_members)
+            barrier()
+            s_evt.record()
+            for _ in range(args.steps):
+                ens = model.sample_ensemble(x_dev, args.ensemble_members)
+            e_evt.record()
+            barrier()
+            ms_ens = s_evt.elapsed_time(e_evt) / args.steps
+            del ens
+        model.train()
+
     if world > 1:
-        tms = torch.tensor([ms_resident, ms_e2e], device=dev, dtype=torch.float64)
+        tms = torch.tensor([ms_resident, ms_e2e, ms_ens or 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms_resident, ms_e2e = tms.tolist()
+        ms_resident, ms_e2e, ms_ens_max = tms.tolist()
+        ms_ens = ms_ens_max if ms_ens is not None else None
 
     if rank == 0:
         peaks = measured_peaks()
@@ -251,6 +290,7 @@ def run_ours(args):
                         'peak_source': f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step)",
                         'flops_per_launch': fl / calls, 'avg_launch_ms': ms / calls, 'launches_timed': calls,
                         'share_of_step': ms / (ms_resident * args.steps), 'traffic': None}
+                roof.update(ncu_traffic())
         step_tflops = GFLOP_FWD_BWD_PER_SAMPLE * global_batch / 1e3 / (ms_resident / 1e3)
         line = {
             'metric': 'elbo_train_samples_per_s', 'value': value, 'unit': 'samples/s', 'n_gpus': world,
@@ -265,6 +305,12 @@ def run_ours(args):
             'roofline': roof, 'clocks': clocks, 'last_loss': loss_host,
             'kernel_ms_per_step': {k: round(v['ms'] / args.steps, 3) for k, v in sorted(kinds.items(), key=lambda kv: -kv[1]['ms'])},
         }
+        if ms_ens is not None:
+            line['ensemble'] = {'metric': 'ensemble_member_samples_per_s',
+                                'value': global_batch * args.ensemble_members / (ms_ens / 1e3),
+                                'unit': 'member-samples/s', 'ms_per_step': ms_ens,
+                                'config': {'inputs_per_gpu': B, 'members': args.ensemble_members, 'tile': TILE,
+                                           'sharding': 'inputs over ranks, all members local'}}
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = cpu_reference_steps(1, 1, sample_batch=2)
             line['cpu_baseline'] = cb
@@ -282,6 +328,8 @@ def main():
     ap.add_argument('--batch', type=int, default=64, help='per-GPU batch')
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--ensemble-members', type=int, default=100,
+                    help='members per input of the secondary ensemble metric (0 disables it)')
     ap.add_argument('--no-profile-calls', dest='profile_calls', action='store_false')
     args = ap.parse_args()
     if args.impl == 'reference':
