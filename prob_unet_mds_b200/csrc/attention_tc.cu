@@ -281,7 +281,7 @@ constexpr int A2_KV_STAGES = 3;
 #ifndef A2_POLY_EVERY
 #define A2_POLY_EVERY 4               // every 4th exponential of a row goes to the FMA pipe (ex2_poly)
 #endif
-constexpr int A2_SMEM = 2 * AT_TILE /*Q0,Q1*/ + A2_KV_STAGES * 2 * AT_TILE /*K,V*/ + 2 * 2 * AT_TILE /*P0,P1*/ + 1024 + 256;
+constexpr int A2_SMEM = 2 * AT_TILE /*Q0,Q1*/ + A2_KV_STAGES * 2 * AT_TILE /*K,V*/ + 1024 + 256;
 
 __global__ void __launch_bounds__(384, 1)
 attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p) {
@@ -289,8 +289,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdPara
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;                                        // q tile t at + t*TILE
     uint8_t* sKV = sQ + 2 * AT_TILE;                           // stage s: K at +s*2*TILE, V at +s*2*TILE + TILE
-    uint8_t* sP = sKV + A2_KV_STAGES * 2 * AT_TILE;            // q tile t at + t*2*TILE (two 64-key blocks)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * 2 * AT_TILE);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + A2_KV_STAGES * 2 * AT_TILE);
     uint64_t* q_full = bars;                       // 1
     uint64_t* kv_full = bars + 1;                  // [2]
     uint64_t* kv_empty = kv_full + A2_KV_STAGES;   // [2]
@@ -334,6 +333,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdPara
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
     const uint32_t tS = tmem_base;           // S[t] at + t*128
     const uint32_t tO = tmem_base + 256;     // O[t] at + t*64
+    const uint32_t tP = tmem_base + 384;     // P[t] at + t*64: bf16 pairs, the A operand of O = P V (never in smem)
 
     if (warp == 0) {
         if (lane == 0) {
@@ -392,11 +392,10 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdPara
                     if (more) issue_s(t, smem_u32(sKV + nstage * 2 * AT_TILE));
                     mbar_wait(smem_u32(&o_empty[t]), jp ^ 1);
                     tc_fence_after();
-                    const uint32_t p_addr = smem_u32(sP + t * 2 * AT_TILE);
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
-                        mma_f16_ss(tO + t * 64, smem_desc_sw128(p_addr + (k >> 2) * AT_TILE + (k & 3) * 32, 16, 1024),
-                                   smem_desc_sw128(v_addr + k * 2048, 8192, 1024), IDESC_O, k ? 1u : 0u);
+                        mma_f16_ts(tO + t * 64, tP + t * 64 + k * 8, smem_desc_sw128(v_addr + k * 2048, 8192, 1024),
+                                   IDESC_O, k ? 1u : 0u);
                     mma_commit(smem_u32(&o_full[t]));
                 }
                 mma_commit(smem_u32(&kv_empty[stage]));
@@ -414,7 +413,6 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdPara
         float acc[AT_D];
 #pragma unroll
         for (int d = 0; d < AT_D; ++d) acc[d] = 0.f;
-        uint8_t* pb = sP + t * 2 * AT_TILE;
         float corr_prev = 1.f;
         // acc = acc * corr + O_jj, with O_jj read back from TMEM (also means P_jj has been consumed by the MMA)
         auto accumulate = [&](int jj, float corr) {
@@ -463,21 +461,18 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdPara
                     pv[i] = (i % A2_POLY_EVERY == A2_POLY_EVERY - 1) ? ex2_poly(x) : ex2_approx(x);
                     rs += pv[i];
                 }
-                uint8_t* kb_base = pb + (c >> 6) * AT_TILE + r * 128;
-                const int chunk0 = (c & 63) >> 3;
+                uint32_t pk[16];
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    uint4 pk;
-                    __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) hp[e] = __floats2bfloat162_rn(pv[g * 8 + 2 * e], pv[g * 8 + 2 * e + 1]);
-                    *reinterpret_cast<uint4*>(kb_base + (((chunk0 + g) ^ (r & 7)) << 4)) = pk;
+                for (int e = 0; e < 16; ++e) {
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(pv[2 * e], pv[2 * e + 1]);
+                    pk[e] = *reinterpret_cast<const uint32_t*>(&h2);
                 }
+                tmem_st16(tP + lane_off + t * 64 + (c >> 1), pk);
             }
             l = l * corr + rs;
             m = m_new;
+            tc_wait_st();
             tc_fence_before();
-            fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(smem_u32(&s_empty[t]));
