@@ -558,14 +558,25 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
 // accumulators cuts it by 25-33 %:
 //   MODE 1: two Cout tiles (256 output channels) share the activation tile  (Cout % 256 == 0)
 //   MODE 2: two filter taps share the dy tile                                (3x3 layers with Cout == 128)
-// TMEM: accumulator 0 at column 0, accumulator 1 at column 256 (no double buffering: the K loops are hundreds of
-// blocks long, the epilogue is a negligible tail).
+//   MODE 3: the three taps of one filter row share the dy tile AND one activation halo tile (18 x 4 pixels instead
+//           of three shifted 16 x 4 tiles): each tap's operand is a window of the halo tile, addressed by starting
+//           the MN-major descriptor at pixel (row * 18 + dx + 1) -- 34 KB per 3 MMA blocks instead of 48 KB per 2.
+//           Needs 3 accumulators of BN <= 128 columns.
+// TMEM: accumulator a at column a * 256 (MODE 1, 2) or a * 128 (MODE 3); no double buffering: the K loops are hundreds
+// of blocks long, the epilogue is a small tail.
 // ------------------------------------------------------------------------------------------------
+constexpr int WG_HALO_W = WG_TW + 2;
+constexpr int WG_HALO = WG_HALO_W * WG_TH * 128;     // one [18 x 4 px][64 ch] halo sub-tile = 9216 B (9 swizzle atoms)
+
 template <int BN, int MODE>
 struct Wgrad2Cfg {
+    static_assert(MODE != 3 || BN <= 128, "MODE 3 keeps three accumulators of BN columns in 512 TMEM columns");
+    static constexpr int NACC = (MODE == 3) ? 3 : 2;
+    static constexpr int ACC_STRIDE = (MODE == 3) ? 128 : 256;
     static constexpr int A_SUBS = (MODE == 1) ? 4 : 2;
     static constexpr int B_SUBS = ((MODE == 1) ? 1 : 2) * (BN / 64);
-    static constexpr int STAGE_BYTES = (A_SUBS + B_SUBS) * WG_SUB;
+    static constexpr int B_BYTES = (MODE == 3) ? (BN / 64) * WG_HALO : B_SUBS * WG_SUB;
+    static constexpr int STAGE_BYTES = A_SUBS * WG_SUB + B_BYTES;
     static constexpr int MAX_STAGES = (227 * 1024 - 1280) / STAGE_BYTES;
     static constexpr int STAGES = MAX_STAGES > 6 ? 6 : MAX_STAGES;
     static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
@@ -615,7 +626,7 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
     const int Ctot = p.C0 + p.C1;
-    const int tap_groups = (MODE == 2) ? (p.taps + 1) / 2 : p.taps;
+    const int tap_groups = (MODE == 2) ? (p.taps + 1) / 2 : (MODE == 3) ? 3 : p.taps;
     const int co_groups = (MODE == 1) ? (p.co_tiles + 1) / 2 : p.co_tiles;
 
     // item -> (split, tap group, co group, ci tile)
@@ -649,13 +660,25 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant
                     const int x0 = bx * WG_TW, y0 = by * WG_TH;
                     mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
                     const uint32_t fb = smem_u32(&full[stage]);
-                    mbar_expect_tx(fb, A_BYTES2 + ntap * B_ONE + ((MODE == 1) ? 0 : 0));
+                    mbar_expect_tx(fb, A_BYTES2 + ((MODE == 3) ? Cfg::B_BYTES : ntap * B_ONE));
                     uint8_t* sa = smem + stage * STAGE_BYTES;
                     uint8_t* sb = sa + A_BYTES2;
 #pragma unroll
                     for (int j = 0; j < Cfg::A_SUBS; ++j)
                         tma_load_4d(smem_u32(sa + j * WG_SUB), &tmDY, fb, co0 + j * 64, x0, y0, img);
-                    for (int tp = 0; tp < ntap; ++tp) {
+                    if (MODE == 3) {
+                        // filter row tg (dy = tg - 1): one 18 x 4 halo tile per 64 channels (tmX0 / tmX1 carry that box)
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j) {
+                            const int c = ci_t * BN + j * 64;
+                            uint8_t* dst = sb + j * WG_HALO;
+                            if (c < p.C0)
+                                tma_load_4d(smem_u32(dst), &tmX0, fb, c, x0 - 1, y0 + tg - 1, img);
+                            else
+                                tma_load_4d(smem_u32(dst), &tmX1, fb, c - p.C0, x0 - 1, y0 + tg - 1, img);
+                        }
+                    }
+                    for (int tp = 0; MODE != 3 && tp < ntap; ++tp) {
                         const int tap = tap0 + tp;
                         const int dy = (p.ksize == 3) ? tap / 3 - 1 : 0;
                         const int dx = (p.ksize == 3) ? tap % 3 - 1 : 0;
@@ -701,7 +724,14 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint32_t acc_flag = (first && k == 0) ? 0u : 1u;
-                        if (MODE == 1) {
+                        if (MODE == 3) {
+                            const uint64_t ad = smem_desc_sw128(a_addr + k * 2048, WG_SUB, 1024);
+#pragma unroll
+                            for (int t = 0; t < 3; ++t)     // tap dx = t - 1: window starts at halo pixel (k, t)
+                                mma_f16_ss(tmem_base + t * Cfg::ACC_STRIDE, ad,
+                                           smem_desc_sw128(b_addr + (k * WG_HALO_W + t) * 128, WG_HALO, 1024), IDESC,
+                                           acc_flag);
+                        } else if (MODE == 1) {
                             const uint64_t bd = smem_desc_sw128(b_addr + k * 2048, WG_SUB, 1024);
                             mma_f16_ss(tmem_base, smem_desc_sw128(a_addr + k * 2048, WG_SUB, 1024), bd, IDESC, acc_flag);
                             mma_f16_ss(tmem_base + 256, smem_desc_sw128(a_addr + 2 * WG_SUB + k * 2048, WG_SUB, 1024), bd,
@@ -731,12 +761,12 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
             int split, tg, cg, ci_t;
             decode(item, split, tg, cg, ci_t);
-            const int tap0 = (MODE == 2) ? 2 * tg : tg;
-            const int ntap = (MODE == 2 && tap0 + 1 < p.taps) ? 2 : 1;
+            const int tap0 = (MODE == 2) ? 2 * tg : (MODE == 3) ? 3 * tg : tg;
+            const int ntap = (MODE == 3) ? 3 : (MODE == 2 && tap0 + 1 < p.taps) ? 2 : 1;
             mbar_wait(smem_u32(tfull), it & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
+            for (int half = 0; half < Cfg::NACC; ++half) {
                 int co, tap;
                 if (MODE == 1) {
                     co = cg * 256 + half * 128 + q * 32 + lane;
@@ -746,7 +776,7 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant
                     co = cg * 128 + q * 32 + lane;
                     tap = tap0 + half;
                 }
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + half * 256;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + half * Cfg::ACC_STRIDE;
 #pragma unroll 1
                 for (int c = 0; c < BN; c += 32) {
                     uint32_t v[32];
@@ -868,7 +898,7 @@ static int wgrad_tc_launch_bn(const PuWgradArgs* a, cudaStream_t st) {
     p.ci_tiles = cdiv(a->C0 + a->C1, BN);
     p.taps = a->ksize * a->ksize;
     const int co_groups = (MODE == 1) ? (p.co_tiles + 1) / 2 : p.co_tiles;
-    const int tap_groups = (MODE == 2) ? (p.taps + 1) / 2 : p.taps;
+    const int tap_groups = (MODE == 2) ? (p.taps + 1) / 2 : (MODE == 3) ? 3 : p.taps;
     int base_items = co_groups * p.ci_tiles * tap_groups;
     // split-K factor: items = base_items * splits are dealt round-robin to one CTA per SM, so pick the split count
     // (up to ~4 waves) whose last wave is fullest -- 2*148/9 = 33 splits would leave a third wave with one item
@@ -897,10 +927,11 @@ static int wgrad_tc_launch_bn(const PuWgradArgs* a, cudaStream_t st) {
     CUtensorMap tDY, tX0, tX1;
     int rc = make_act_tmap(&tDY, a->dy, a->N, a->H, a->W, a->Cout, WG_TW, WG_TH);
     if (rc) return rc;
-    rc = make_act_tmap(&tX0, a->src0, a->N, a->H, a->W, a->C0, WG_TW, WG_TH);
+    const int xbw = (MODE == 3) ? WG_HALO_W : WG_TW;      // MODE 3 loads 18-pixel-wide halo tiles
+    rc = make_act_tmap(&tX0, a->src0, a->N, a->H, a->W, a->C0, xbw, WG_TH);
     if (rc) return rc;
     if (a->C1 > 0)
-        rc = make_act_tmap(&tX1, a->src1, a->N, a->H, a->W, a->C1, WG_TW, WG_TH);
+        rc = make_act_tmap(&tX1, a->src1, a->N, a->H, a->W, a->C1, xbw, WG_TH);
     else
         tX1 = tX0;
     if (rc) return rc;
@@ -927,23 +958,30 @@ static int wgrad_tc_launch_bn(const PuWgradArgs* a, cudaStream_t st) {
 }
 
 template <int BN>
-static int wgrad_tc_pick_mode(const PuWgradArgs* a, cudaStream_t st) {
-    static const int force = getenv("PU_WGRAD_MODE") ? atoi(getenv("PU_WGRAD_MODE")) : -1;   // experiments only
-    int mode = 0;
-    if (a->Cout % 256 == 0) mode = 1;                       // two Cout tiles share the activation tile
-    else if (a->ksize == 3) mode = 2;                       // two taps share the dy tile
-    if (force >= 0) mode = force;
+static int wgrad_tc_pick_mode(const PuWgradArgs* a, cudaStream_t st, int mode) {
     if (mode == 1) return wgrad_tc_launch_bn<BN, 1>(a, st);
     if (mode == 2 && a->ksize == 3) return wgrad_tc_launch_bn<BN, 2>(a, st);
+    if constexpr (BN <= 128) {
+        if (mode == 3 && a->ksize == 3) return wgrad_tc_launch_bn<BN, 3>(a, st);
+    }
     return wgrad_tc_launch_bn<BN, 0>(a, st);
 }
 
 int wgrad_tc_launch(const PuWgradArgs* a, cudaStream_t st) {
-    int Ctot = a->C0 + a->C1;
-    if (Ctot % 256 == 0) return wgrad_tc_pick_mode<256>(a, st);
-    if (Ctot % 192 == 0) return wgrad_tc_pick_mode<192>(a, st);
-    if (Ctot % 128 == 0) return wgrad_tc_pick_mode<128>(a, st);
-    return wgrad_tc_pick_mode<64>(a, st);
+    static const int force = getenv("PU_WGRAD_MODE") ? atoi(getenv("PU_WGRAD_MODE")) : -1;   // experiments only
+    const int Ctot = a->C0 + a->C1;
+    // 3x3 layers take the halo kernel (MODE 3) with 128- or 64-channel activation tiles; 1x1 layers the single
+    // accumulator kernel (measured: MODE 1 / 2 lose to these on every layer of the U-Net, they stay for A/B runs)
+    if (a->ksize == 3 && a->W >= WG_TW && (force < 0 || force == 3)) {
+        if (Ctot % 128 == 0) return wgrad_tc_pick_mode<128>(a, st, 3);
+        return wgrad_tc_pick_mode<64>(a, st, 3);
+    }
+    int mode = 0;
+    if (force >= 0) mode = force;
+    if (Ctot % 256 == 0) return wgrad_tc_pick_mode<256>(a, st, mode);
+    if (Ctot % 192 == 0) return wgrad_tc_pick_mode<192>(a, st, mode);
+    if (Ctot % 128 == 0) return wgrad_tc_pick_mode<128>(a, st, mode);
+    return wgrad_tc_pick_mode<64>(a, st, mode);
 }
 
 }  // namespace pu

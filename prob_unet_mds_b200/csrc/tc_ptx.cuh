@@ -189,6 +189,11 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo
     d |= (uint64_t)2 << 61;
     return d;
 }
+// same for a start address that is not aligned to the 1024-byte swizzle pattern (a window that begins at an arbitrary
+// 128-byte row of a larger TMA box): the row phase goes into the "matrix base offset" field, bits [49,52)
+__device__ __forceinline__ uint64_t smem_desc_sw128_off(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return smem_desc_sw128(saddr, lbo_bytes, sbo_bytes) | ((uint64_t)((saddr >> 7) & 7u) << 49);
+}
 // instruction descriptor for kind::f16 with bf16 A/B and fp32 D (InstrDescriptor in the same header)
 __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N, int a_mn_major, int b_mn_major) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
