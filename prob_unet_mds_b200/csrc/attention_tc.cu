@@ -430,47 +430,72 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdPara
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&o_empty[t]));
         };
+        // Online softmax with a lagging reference.  The exact scheme reads S twice per key tile (row max, then exp); here
+        // tile j > 0 uses the running maximum of tiles < j as its reference, so one pass over S suffices (P may exceed 1,
+        // harmless in bf16 / fp32; O and l are rescaled when the reference moves, as before).  Exactness is kept by a
+        // fallback: if any row of the warp sees a score more than 2^64 above its reference, the warp redoes the tile
+        // with the exact two-pass scheme (S is still in TMEM, P has not been handed to the MMA yet).
+        float m_ref = 0.f;                 // reference of the previous tile's P (== reference of acc and l)
+        auto exp_chunk = [&](int c, float ref, float& rs, float& mxr, uint32_t (&pk)[16]) {
+            uint32_t v[32];
+            tmem_ld32(tS + lane_off + t * 128 + c, v);
+            tc_wait_ld();
+            float pv[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float sv = __uint_as_float(v[i]);
+                mxr = fmaxf(mxr, sv);
+                const float x = fmaf(sv, sc, -ref);
+                pv[i] = (i % A2_POLY_EVERY == A2_POLY_EVERY - 1) ? ex2_poly(x) : ex2_approx(x);
+                rs += pv[i];
+            }
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(pv[2 * e], pv[2 * e + 1]);
+                pk[e] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+        };
         for (int j = 0; j < ntiles; ++j) {
             const uint32_t jp = j & 1;
             mbar_wait(smem_u32(&s_full[t]), jp);
             tc_fence_after();
-            float mx = -INFINITY;
+            float ref = m, rs = 0.f, mxr = -INFINITY;
+            bool exact = (j == 0);
+            uint32_t pkA[16];
+            if (j > 0) accumulate(j - 1, corr_prev);          // P_{j-1} consumed: the P columns may be overwritten
+            if (!exact) {
 #pragma unroll 1
-            for (int c = 0; c < AT_TK; c += 32) {
-                uint32_t v[32];
-                tmem_ld32(tS + lane_off + t * 128 + c, v);
-                tc_wait_ld();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+                for (int c = 0; c < AT_TK; c += 32) {
+                    exp_chunk(c, ref, rs, mxr, pkA);
+                    tmem_st16(tP + lane_off + t * 64 + (c >> 1), pkA);
+                }
+                exact = __any_sync(0xffffffffu, fmaf(mxr, sc, -ref) > 64.f);
             }
-            const float m_new = fmaxf(m, mx * sc);
-            const float corr = ex2_approx(m - m_new);
-            // O_{j-1} (issued while the row max above was being computed) must be folded in before P is overwritten
-            if (j > 0) accumulate(j - 1, corr_prev);
+            if (exact) {
+                // exact two-pass scheme (first tile, or a score far above the lagging reference)
+                mxr = -INFINITY;
+#pragma unroll 1
+                for (int c = 0; c < AT_TK; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tS + lane_off + t * 128 + c, v);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) mxr = fmaxf(mxr, __uint_as_float(v[i]));
+                }
+                ref = fmaxf(m, mxr * sc);
+                rs = 0.f;
+                float dummy = -INFINITY;
+#pragma unroll 1
+                for (int c = 0; c < AT_TK; c += 32) {
+                    exp_chunk(c, ref, rs, dummy, pkA);
+                    tmem_st16(tP + lane_off + t * 64 + (c >> 1), pkA);
+                }
+            }
+            const float corr = (j == 0) ? 1.f : ex2_approx(m_ref - ref);
             corr_prev = corr;
-            float rs = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < AT_TK; c += 32) {
-                uint32_t v[32];
-                tmem_ld32(tS + lane_off + t * 128 + c, v);
-                tc_wait_ld();
-                float pv[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float x = fmaf(__uint_as_float(v[i]), sc, -m_new);
-                    pv[i] = (i % A2_POLY_EVERY == A2_POLY_EVERY - 1) ? ex2_poly(x) : ex2_approx(x);
-                    rs += pv[i];
-                }
-                uint32_t pk[16];
-#pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(pv[2 * e], pv[2 * e + 1]);
-                    pk[e] = *reinterpret_cast<const uint32_t*>(&h2);
-                }
-                tmem_st16(tP + lane_off + t * 64 + (c >> 1), pk);
-            }
             l = l * corr + rs;
-            m = m_new;
+            m_ref = ref;
+            m = fmaxf(m, mxr * sc);        // running maximum over the tiles seen so far
             tc_wait_st();
             tc_fence_before();
             __syncwarp();
@@ -490,7 +515,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdPara
             for (int e = 0; e < 16; ++e) o16[e] = acc[d + e] * inv;
             st16(op + d, o16);
         }
-        p.lse[((long long)n * p.heads + h) * p.T + q0 + t * AT_TQ + r] = (m + log2f(l)) * 0.6931471805599453f;
+        p.lse[((long long)n * p.heads + h) * p.T + q0 + t * AT_TQ + r] = (m_ref + log2f(l)) * 0.6931471805599453f;
     }
 
     tc_fence_before();

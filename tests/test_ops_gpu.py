@@ -344,6 +344,36 @@ def test_attention_tc(N, T, heads):
     assert eb < 1.5e-2
 
 
+def test_attention_tc_score_jumps():
+    """The forward kernel's softmax uses the running maximum of the *previous* key tiles as the reference of the current
+    one and falls back to the exact two-pass scheme when a score exceeds it by more than 2^64.  Build that case: keys in
+    the second and third 128-key tiles whose scores sit ~60 and ~100 nats above everything before them (with different
+    values inside one tile), and compare with the fp32 softmax."""
+    dt = torch.bfloat16
+    N, T, heads = 1, 512, 1
+    Cc = 64
+    qkv = rnd(N, T, 3 * Cc, seed=21)
+    u = torch.zeros(Cc, device=DEV)
+    u[0] = 1.0
+    q = qkv[..., :Cc]
+    q[..., 0] = 4.0 + 0.25 * rnd(N, T, seed=22)            # every query has a component of ~4 along u
+    k = qkv[..., Cc:2 * Cc]
+    k[0, 200] = 120.0 * u                                   # score ~ 4*120/8 = 60 above the rest (tile 1)
+    k[0, 201] = 100.0 * u                                   # a second, different large score in the same tile
+    k[0, 300] = 200.0 * u                                   # tile 2: jumps again, by ~40 nats over tile 1
+    k[0, 400] = 199.0 * u                                   # tile 3: close to the maximum, no fallback needed
+    qkv = qkv.to(dt).float()
+    ref = _attn_ref(qkv, heads)
+    out, lse = ops.attention_fwd(qkv.to(dt), heads, flags=L.CONV_FORCE_TC)
+    qq, kk, _ = [t.reshape(N, T, heads, 64).permute(0, 2, 1, 3) for t in qkv.split(Cc, dim=-1)]
+    lse_ref = torch.logsumexp(qq @ kk.transpose(-1, -2) / 8.0, dim=-1)
+    e = rel_err(out, ref)
+    print(f'attention_tc score jumps: rel {e:.3e}, lse max err {max_err(lse, lse_ref):.3e}')
+    assert torch.isfinite(out.float()).all()
+    assert e < 6e-3
+    assert max_err(lse, lse_ref) < 2e-3 * lse_ref.abs().max().item()
+
+
 def test_encoder_glue():
     x = rnd(2, 64, 8, 8, seed=1)
     xs = nhwc(x, torch.float32)
