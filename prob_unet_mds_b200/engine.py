@@ -423,15 +423,19 @@ class GaussianEngine:
             acts.append((x, r))
             if not last:
                 x = ops.avgpool2(r)
-        # AvgPool2d(2) followed by the global mean == global mean of r (H, W even)
-        if acts[-1][1].shape[1] % 2 or acts[-1][1].shape[2] % 2:
-            raise ValueError('prior/posterior encoder needs H, W divisible by 2**len(num_filters)')
-        m = ops.global_mean(acts[-1][1])
+        # AvgPool2d(2) followed by the global mean == global mean of r when H, W are even; for odd sizes (inputs that are
+        # multiples of 8 but not of 16) AvgPool2d floors, i.e. the last row / column never reaches the mean
+        r_last = acts[-1][1]
+        h2, w2 = r_last.shape[1] // 2 * 2, r_last.shape[2] // 2 * 2
+        if h2 == 0 or w2 == 0:
+            raise ValueError('prior/posterior encoder: input too small for len(num_filters) 2x pools')
+        crop = (h2, w2) if (h2, w2) != tuple(r_last.shape[1:3]) else None
+        m = ops.global_mean(r_last[:, :h2, :w2, :].contiguous() if crop else r_last)
         net = self.net
         Lz = net.latent_dim
         mu = ops.heads_fwd(m, net.conv_mu.weight, net.conv_mu.bias)
         ls = ops.heads_fwd(m, net.conv_log_sigma.weight, net.conv_log_sigma.bias)
-        tape = dict(acts=acts, m=m) if save else None
+        tape = dict(acts=acts, m=m, crop=crop) if save else None
         return mu, ls, tape
 
     def backward(self, tape, dmu, dls, grads):
@@ -453,7 +457,12 @@ class GaussianEngine:
             c = convs[i]
             x, r = tape['acts'][i]
             if i == len(convs) - 1:
-                dr = ops.relu_mean_bwd(dm, r)
+                if tape.get('crop'):
+                    h2, w2 = tape['crop']
+                    dr = torch.zeros_like(r)
+                    dr[:, :h2, :w2, :] = ops.relu_mean_bwd(dm, r[:, :h2, :w2, :].contiguous())
+                else:
+                    dr = ops.relu_mean_bwd(dm, r)
             else:
                 dr = ops.relu_pool_bwd(dp, r)
             dwp = ops.conv2d_wgrad(x, dr, 3)
