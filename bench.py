@@ -189,7 +189,11 @@ def run_ours(args):
     model.load_state_dict(synth.make_weights(synth.load_schema(f'schema_probunet_L{LATENT}.json'), seed=0))
     model.set_precision(args.precision)
     model.train()
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, fused=True)
+    if args.torch_adamw:
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, fused=True)
+    else:
+        from prob_unet_mds_b200 import AdamW          # one-launch multi-tensor AdamW, torch.optim.AdamW semantics
+        opt = AdamW(model.parameters(), lr=1e-3)
     # gradient all-reduce (SUM) overlapped with backward; attaches itself to the model
     ddp = parallel.DataParallel(model) if world > 1 else None  # noqa: F841
 
@@ -296,7 +300,9 @@ def run_ours(args):
             'metric': 'elbo_train_samples_per_s', 'value': value, 'unit': 'samples/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_resident, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16' if args.precision == 'bf16' else 'f32',
-            'data': 'synthetic', 'config': workload_config(world, B),
+            'data': 'synthetic',
+            'config': dict(workload_config(world, B), optimizer='torch.optim.AdamW(fused=True)' if args.torch_adamw
+                           else 'prob_unet_mds_b200.AdamW (pu_adamw_multi)'),
             'e2e': {'value': e2e_value, 'unit': 'samples/s', 'ms_per_step': ms_e2e,
                     'h2d_bytes_per_step': int(x_pin.numel() * 4 + t_pin.numel() * 4), 'd2h_bytes_per_step': 4},
             'gpu_launches': launches,
@@ -328,6 +334,8 @@ def main():
     ap.add_argument('--batch', type=int, default=64, help='per-GPU batch')
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--torch-adamw', action='store_true',
+                    help="use torch.optim.AdamW(fused=True) instead of the package's multi-tensor AdamW")
     ap.add_argument('--ensemble-members', type=int, default=100,
                     help='members per input of the secondary ensemble metric (0 disables it)')
     ap.add_argument('--no-profile-calls', dest='profile_calls', action='store_false')

@@ -218,6 +218,16 @@ int pu_fcomb_z_bwd(const float* rmean, float hw, const float* z, const float* w0
 /* ---------------- optimiser (fused AdamW, torch.optim.AdamW semantics, main.py:95) ---------------- */
 int pu_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
              float eps, float weight_decay, int step, void* stream);
+/* Multi-tensor form: one launch for the whole model.  `chunks` is a DEVICE array; each entry is a run of n <= 65536
+ * fp32 elements of one parameter (device addresses of the parameter, its gradient and the two moment buffers at the same
+ * offset).  Replaces the 446-tensor loop of torch.optim.AdamW.step (main.py:95, train_prob_unet_model.py:92). */
+typedef struct PuAdamWChunk {
+    unsigned long long p, g, m, v;
+    int n;
+    int pad_;
+} PuAdamWChunk;
+int pu_adamw_multi(const PuAdamWChunk* chunks, int nchunks, double lr, double beta1, double beta2, double eps,
+                   double weight_decay, int step, void* stream);
 
 #ifdef __cplusplus
 }
