@@ -229,6 +229,22 @@ typedef struct PuAdamWChunk {
 int pu_adamw_multi(const PuAdamWChunk* chunks, int nchunks, double lr, double beta1, double beta2, double eps,
                    double weight_decay, int step, void* stream);
 
+/* ---------------- data preparation ----------------
+ * pu_climex_prepare: climex2torch.__getitem__ (climex_utils.py:122-162) for a batch on the device:
+ *   lr = AvgPool2d(scale)(hr); lrinterp = interpolate(lr, scale_factor=scale, mode="bilinear");
+ *   inputs = stand(lrinterp); targets = stand(hr) - stand(lrinterp).            All tensors fp32 NCHW.
+ * Statistics (climex_utils.py:165-195): PERPIXEL s0 = mean, s1 = std as [C][H][W]; PERTIMESTEP s0 = mean, s1 = std as
+ * [N][C]; MINMAX s0 = min, s1 = max as [N][C]; NONE: null.  eps is the reference's 1e-10.
+ * pu_climex_residual_to_hr: climex_utils.py:198-211, hr_pred = lrinterp + residual * (s1 [- s0] + eps). */
+#define PU_STAND_NONE 0
+#define PU_STAND_PERPIXEL 1
+#define PU_STAND_PERTIMESTEP 2
+#define PU_STAND_MINMAX 3
+int pu_climex_prepare(const float* hr, const float* s0, const float* s1, int stand_mode, float eps, int N, int C, int H,
+                      int W, int scale, float* lr, float* lrinterp, float* inputs, float* targets, void* stream);
+int pu_climex_residual_to_hr(const float* residual, const float* lrinterp, const float* s0, const float* s1, int stand_mode,
+                             float eps, int N, int C, int H, int W, float* hr_pred, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

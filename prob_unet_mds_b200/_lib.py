@@ -92,6 +92,10 @@ _SIGNATURES = {
                                c_int, c_void_p]),
     'pu_adamw': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_float, c_float,
                          c_int, c_void_p]),
+    'pu_climex_prepare': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_void_p]),
+    'pu_climex_residual_to_hr': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_int, c_int, c_int, c_int,
+                                         c_void_p, c_void_p]),
     'pu_adamw_multi': (c_int, [c_void_p, c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, c_int,
                                c_void_p]),
 }

@@ -116,9 +116,36 @@ def eager(args):
         torch.cuda.empty_cache()
 
 
+def prepare(args):
+    """Device-side ClimEx sample preparation for the bench batch, beside the reference's per-item CPU path."""
+    import time
+    from oracle import climex_oracle as CO
+    from prob_unet_mds_b200 import data
+    B = args.inputs
+    g = torch.Generator().manual_seed(3)
+    hr = torch.randn(B, 3, 128, 128, generator=g) * 3 + 1
+    stats = CO.compute_stats(hr, 'perpixel')
+    hr_d = hr.cuda()
+    st_d = [s.cuda() for s in stats]
+    ms = timed(lambda: data.prepare_batch(hr_d, 'perpixel', st_d), 50, 10)
+    out = data.prepare_batch(hr_d, 'perpixel', st_d)
+    res = torch.randn_like(hr_d)
+    ms_inv = timed(lambda: data.residual_to_hr(res, out['lrinterp'], 'perpixel', st_d), 50, 10)
+    t0 = time.perf_counter()
+    for i in range(B):                      # what the DataLoader does: one __getitem__ per sample
+        CO.prepare_batch(hr[i:i + 1], 'perpixel', stats)
+    cpu_s = time.perf_counter() - t0
+    nbytes = hr.numel() * 4 * 4 + stats[0].numel() * 8
+    print(json.dumps({'metric': 'climex_prepare_samples_per_s', 'value': B / (ms / 1e3), 'ms_per_batch': ms,
+                      'gbs': nbytes / ms / 1e6, 'residual_to_hr_ms': ms_inv,
+                      'cpu_baseline': {'value': B / cpu_s, 'unit': 'samples/s', 'kind': 'port',
+                                       'cores': torch.get_num_threads()},
+                      'config': {'batch': B, 'tile': 128, 'standardization': 'perpixel'}}), flush=True)
+
+
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
-    ap.add_argument('what', nargs='+', choices=['ensemble', 'detunet', 'eager'])
+    ap.add_argument('what', nargs='+', choices=['ensemble', 'detunet', 'eager', 'prepare'])
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=2)
     ap.add_argument('--inputs', type=int, default=64)
@@ -127,4 +154,4 @@ if __name__ == '__main__':
     ap.add_argument('--eager-batch', type=int, default=16)
     a = ap.parse_args()
     for w in a.what:
-        {'ensemble': ensemble, 'detunet': detunet, 'eager': eager}[w](a)
+        {'ensemble': ensemble, 'detunet': detunet, 'eager': eager, 'prepare': prepare}[w](a)
