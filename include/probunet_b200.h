@@ -245,6 +245,14 @@ int pu_climex_prepare(const float* hr, const float* s0, const float* s1, int sta
 int pu_climex_residual_to_hr(const float* residual, const float* lrinterp, const float* s0, const float* s1, int stand_mode,
                              float eps, int N, int C, int H, int W, float* hr_pred, void* stream);
 
+/* ---------------- ensemble metric ----------------
+ * trainmodel.crps_empirical (trainmodel.py:66-110): out = mean_s |pred_s - truth| - sum_{i<j} |pred_i - pred_j| / S^2.
+ * Element (o, r), o < outer, r < inner: members at pred[o * outer_stride + s * member_stride + r], truth / out at
+ * [o * inner + r].  Reference layout pred [S, ...]: outer = 1, member_stride = inner.  Ensemble [B, S, C, H, W] against
+ * truth [B, C, H, W]: outer = B, inner = member_stride = C*H*W, outer_stride = S*C*H*W. */
+int pu_crps_empirical(const float* pred, const float* truth, float* out, int S, long long outer, long long inner,
+                      long long member_stride, long long outer_stride, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

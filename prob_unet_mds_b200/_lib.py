@@ -96,6 +96,7 @@ _SIGNATURES = {
                                   c_void_p, c_void_p, c_void_p, c_void_p]),
     'pu_climex_residual_to_hr': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_int, c_int, c_int, c_int,
                                          c_void_p, c_void_p]),
+    'pu_crps_empirical': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_ll, c_ll, c_ll, c_ll, c_void_p]),
     'pu_adamw_multi': (c_int, [c_void_p, c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, c_int,
                                c_void_p]),
 }

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libprobunet_b200.so')
 SOURCES = ['api.cu', 'layout.cu', 'conv_simple.cu', 'conv_tc.cu', 'gn.cu', 'attention_simple.cu', 'attention_tc.cu',
-           'latent.cu', 'fcomb.cu', 'fcomb_tc.cu', 'optim.cu', 'data.cu']
+           'latent.cu', 'fcomb.cu', 'fcomb_tc.cu', 'optim.cu', 'data.cu', 'metrics.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 

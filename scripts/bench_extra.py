@@ -143,9 +143,40 @@ def prepare(args):
                       'config': {'batch': B, 'tile': 128, 'standardization': 'perpixel'}}), flush=True)
 
 
+def crps(args):
+    """Empirical CRPS of the bench ensemble: the fused kernel, the reference function run on the same GPU
+    by PyTorch (torch.sort over the member dimension), and the reference function on the host cores (bounded sample)."""
+    import time
+    from oracle import metrics_oracle as MO
+    from prob_unet_mds_b200 import metrics
+    B, S = args.inputs, args.members
+    ens = torch.randn(B, S, 3, 128, 128, device='cuda')
+    truth = torch.randn(B, 3, 128, 128, device='cuda')
+    ms = timed(lambda: metrics.crps_ensemble(ens, truth), args.steps, args.warmup)
+
+    def torch_gpu():
+        pred = ens.transpose(0, 1)
+        p = pred.sort(dim=0).values
+        diff = p[1:] - p[:-1]
+        w = (torch.arange(1, S, device='cuda') * torch.arange(S - 1, 0, -1, device='cuda')).float()
+        w = w.reshape(w.shape + (1,) * (diff.dim() - 1))
+        return (p - truth).abs().mean(0) - (diff * w).sum(0) / S ** 2
+    ms_t = timed(torch_gpu, args.steps, args.warmup)
+    nb = 2
+    e_cpu, t_cpu = ens[:nb].transpose(0, 1).contiguous().cpu(), truth[:nb].cpu()
+    t0 = time.perf_counter()
+    MO.crps_empirical(e_cpu, t_cpu)
+    cpu_s = time.perf_counter() - t0
+    print(json.dumps({'metric': 'crps_member_samples_per_s', 'value': B * S / (ms / 1e3), 'ms_per_call': ms,
+                      'gbs_read': ens.numel() * 4 / ms / 1e6, 'torch_same_gpu_ms': ms_t,
+                      'cpu_baseline': {'value': nb * S / cpu_s, 'unit': 'member-samples/s', 'kind': 'port',
+                                       'cores': torch.get_num_threads(), 'sample': f'{nb} inputs x {S} members'},
+                      'config': {'inputs': B, 'members': S, 'tile': 128}}), flush=True)
+
+
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
-    ap.add_argument('what', nargs='+', choices=['ensemble', 'detunet', 'eager', 'prepare'])
+    ap.add_argument('what', nargs='+', choices=['ensemble', 'detunet', 'eager', 'prepare', 'crps'])
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=2)
     ap.add_argument('--inputs', type=int, default=64)
@@ -154,4 +185,4 @@ if __name__ == '__main__':
     ap.add_argument('--eager-batch', type=int, default=16)
     a = ap.parse_args()
     for w in a.what:
-        {'ensemble': ensemble, 'detunet': detunet, 'eager': eager, 'prepare': prepare}[w](a)
+        {'ensemble': ensemble, 'detunet': detunet, 'eager': eager, 'prepare': prepare, 'crps': crps}[w](a)
