@@ -52,3 +52,29 @@ def test_no_cpu_fallback():
         m.elbo(x, t)
     with pytest.raises(RuntimeError, match='no CPU path'):
         m(x, training=False)
+
+
+def test_checkpoint_roundtrip_in_reference_format(tmp_path):
+    """{name}.pt is a plain state_dict and {name}_optimizer.pt a plain optimizer state_dict, exactly what
+    baseline/main.py:108-109 writes; both load back, and a reference-style file (bare torch.save of a state_dict) loads."""
+    from prob_unet_mds_b200 import ProbabilisticUNet, checkpoint
+    m = ProbabilisticUNet(3, 3, latent_dim=6)
+    m.load_state_dict(synth.make_weights(synth.load_schema('schema_probunet_L6.json'), seed=3))
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-4)
+    for p in list(m.parameters())[:5]:
+        p.grad = torch.ones_like(p)
+    opt.step()
+    checkpoint.save(str(tmp_path), 'probunet', m, opt, epoch=7, global_step=123)
+    raw = torch.load(tmp_path / 'probunet.pt')
+    assert [(k, tuple(v.shape)) for k, v in raw.items()] == synth.load_schema('schema_probunet_L6.json')
+    m2 = ProbabilisticUNet(3, 3, latent_dim=6)
+    opt2 = torch.optim.AdamW(m2.parameters(), lr=1e-4)
+    state = checkpoint.load(str(tmp_path), 'probunet', m2, opt2)
+    assert state['epoch'] == 7 and state['global_step'] == 123
+    for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
+    s1, s2 = opt.state_dict()['state'], opt2.state_dict()['state']
+    assert s1.keys() == s2.keys() and all(torch.equal(s1[i]['exp_avg'], s2[i]['exp_avg']) for i in s1)
+    # a checkpoint written the reference's way
+    torch.save(synth.make_weights(synth.load_schema('schema_probunet_L6.json'), seed=4), tmp_path / 'ref.pt')
+    assert checkpoint.load(str(tmp_path), 'ref', m2) == {}
