@@ -3,7 +3,7 @@
 # gpu__time_duration.sum for every launch.  Numbers printed under ncu are never bench values.
 set -u
 mkdir -p gpurun_out
-CMD="python bench.py --steps 1 --warmup 1 --batch 64 --no-cpu-baseline --no-profile-calls"
+CMD="python bench.py --steps 1 --warmup 1 --batch 64 --no-cpu-baseline --no-profile-calls --ensemble-members 0"
 $CMD > gpurun_out/plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 12000 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list exit=$?"
