@@ -583,9 +583,6 @@ struct AttnBwdParams {
     __nv_bfloat16* dqkv;      // [N*T][3C]
 };
 
-__device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
-    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
-}
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }

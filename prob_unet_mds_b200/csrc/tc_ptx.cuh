@@ -165,18 +165,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "memory");
 }
 
-// 16 lanes x 32 columns of fp32 in the mma-fragment layout (.16x256b, 4 repetitions of 8 columns): for repetition j,
-// thread t gets r[4j+0..1] = (lane t/4, columns 8j + 2(t%4) + {0,1}) and r[4j+2..3] = (lane t/4 + 8, same columns)
-__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-}
-
 // ---------------- descriptors ----------------
 // UMMA shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start>>4 [0,14),
 // LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout type [61,64) (2 = SWIZZLE_128B).
@@ -189,11 +177,10 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo
     d |= (uint64_t)2 << 61;
     return d;
 }
-// same for a start address that is not aligned to the 1024-byte swizzle pattern (a window that begins at an arbitrary
-// 128-byte row of a larger TMA box): the row phase goes into the "matrix base offset" field, bits [49,52)
-__device__ __forceinline__ uint64_t smem_desc_sw128_off(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return smem_desc_sw128(saddr, lbo_bytes, sbo_bytes) | ((uint64_t)((saddr >> 7) & 7u) << 49);
-}
+// Note on unaligned starts: the 128B swizzle is a pure function of the shared-memory address bits (bits [4,7) ^= bits
+// [7,10)), for TMA writes and for UMMA operand reads alike.  A descriptor may therefore start at any 128-byte row of a
+// larger swizzled TMA box (the halo windows of the weight-gradient kernel do) with the base-offset field left at 0;
+// setting that field to the row phase was measured to give wrong results.
 // instruction descriptor for kind::f16 with bf16 A/B and fp32 D (InstrDescriptor in the same header)
 __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N, int a_mn_major, int b_mn_major) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
