@@ -52,6 +52,8 @@ class ClockSampler(threading.Thread):
         self._halt = threading.Event()
 
     def run(self):
+        if self._run_nvml():
+            return
         q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
         while not self._halt.is_set():
@@ -63,6 +65,26 @@ class ClockSampler(threading.Thread):
             except Exception:  # noqa: BLE001
                 pass
             self._halt.wait(0.2)
+
+    def _run_nvml(self):
+        """Same columns through NVML (no subprocess, one sample every 20 ms); False if pynvml is unusable."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            return False
+        bits = (('hw_slowdown', 0x8), ('hw_thermal_slowdown', 0x40), ('sw_thermal_slowdown', 0x20), ('sw_power_cap', 0x4))
+        while not self._halt.is_set():
+            try:
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append([str(sm), str(mx)] + ['Active' if r & b else 'Not Active' for _, b in bits])
+            except Exception:  # noqa: BLE001
+                pass
+            self._halt.wait(0.02)
+        return True
 
     def stop(self):
         self._halt.set()
