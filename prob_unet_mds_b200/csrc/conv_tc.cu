@@ -900,22 +900,33 @@ static int wgrad_tc_launch_bn(const PuWgradArgs* a, cudaStream_t st) {
     const int co_groups = (MODE == 1) ? (p.co_tiles + 1) / 2 : p.co_tiles;
     const int tap_groups = (MODE == 2) ? (p.taps + 1) / 2 : (MODE == 3) ? 3 : p.taps;
     int base_items = co_groups * p.ci_tiles * tap_groups;
-    // split-K factor: items = base_items * splits are dealt round-robin to one CTA per SM, so pick the split count
-    // (up to ~4 waves) whose last wave is fullest -- 2*148/9 = 33 splits would leave a third wave with one item
+    // split-K factor: items = base_items * splits are dealt round-robin to one CTA per SM.  Cost model per item:
+    // K blocks at max(MMA, operand feed) cycles each, plus the epilogue -- the fp32 reductions of the whole accumulator
+    // tile, which are not overlapped (one accumulator stage) and drain at the L2 atomic rate.  More splits fill the
+    // last wave better but multiply the epilogues; pick the split count with the smallest modelled time (ties: fewer).
+    constexpr int NACC = (MODE == 0) ? 1 : (MODE == 3) ? 3 : 2;
+    const double op_bytes = (MODE == 0)   ? (2 + BN / 64) * 8192.0
+                            : (MODE == 1) ? (4 + BN / 64) * 8192.0
+                            : (MODE == 2) ? (2 + 2 * (BN / 64)) * 8192.0
+                                          : 16384.0 + (BN / 64) * 9216.0;
+    const double t_mma = NACC * 2.0 * BN;                        // 4 x (128 x BN x 16) MMAs per accumulator and block
+    const double t_feed = op_bytes / 48.0;                       // measured L2 -> shared-memory rate, B/clk/SM
+    const double t_blk = t_mma > t_feed ? t_mma : t_feed;
+    const double t_epi = NACC * 128.0 * BN * 4.0 / 21.0 + 2000.0;   // measured L2 reduction rate, B/clk/SM
     long long max_split = cdivll(p.px_blocks, 8);   // at least 8 K-blocks (512 pixels) per item
     if (max_split < 1) max_split = 1;
     const int sms = num_sms();
-    long long hi = cdivll(4LL * sms, base_items);
+    long long hi = cdivll(8LL * sms, base_items);
     if (hi > max_split) hi = max_split;
     if (hi < 1) hi = 1;
     long long splits = 1;
-    double best = -1.0;
+    double best = 1e300;
     for (long long s = 1; s <= hi; ++s) {
         const long long items = (long long)base_items * s;
         const long long waves = cdivll(items, sms);
-        const double eff = (double)items / (double)(waves * sms);
-        if (eff > best + 1e-9) {      // ties: fewer splits (fewer partial-sum reductions)
-            best = eff;
+        const double t = (double)waves * ((double)cdivll(p.px_blocks, s) * t_blk + t_epi);
+        if (t < best * (1.0 - 1e-9)) {
+            best = t;
             splits = s;
         }
     }
