@@ -33,3 +33,13 @@ def test_error_reporting_without_gpu():
     rc = lib.pu_rsample(None, None, None, None, None, None, 0, None)
     assert rc == -1
     assert b'pu_rsample' in lib.pu_last_error()
+
+
+def test_every_cuda_source_is_built():
+    """build.SOURCES must list every .cu under csrc/ (a forgotten file would silently drop its kernels from the .so)."""
+    import os
+    from prob_unet_mds_b200 import build
+    on_disk = sorted(f for f in os.listdir(build.CSRC) if f.endswith('.cu'))
+    assert sorted(build.SOURCES) == on_disk
+    assert '-gencode' in build.NVCC_FLAGS and 'arch=compute_100a,code=sm_100a' in build.NVCC_FLAGS
+    assert '-lineinfo' in build.NVCC_FLAGS
