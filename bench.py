@@ -146,7 +146,8 @@ def run_reference(args):
         return
     steps = max(1, min(args.steps, 3))
     warm = 1
-    cb, sec = cpu_reference_steps(steps, warm, sample_batch=2)
+    # torchrun exports OMP_NUM_THREADS=1 for every rank; this arm runs on rank 0 alone and is meant to use the host
+    cb, sec = cpu_reference_steps(steps, warm, sample_batch=2, threads=os.cpu_count() or 1)
     line = {
         'impl': 'reference', 'metric': 'elbo_train_samples_per_s', 'value': cb['value'], 'unit': 'samples/s',
         'n_gpus': args.gpus, 'steps': steps, 'warmup': warm, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
