@@ -77,8 +77,8 @@ typedef struct PuConvArgs {
     const float* bias;    /* fp32 or NULL (networks.py:88-89 x.add_(b))                                */
     const void* residual; /* NHWC [N,H,W,Cout] added in the epilogue or NULL (networks.py:176,183)     */
     void* out;            /* NHWC [N,H,W,Cout]; may alias residual                                     */
-    double* gn_stats;     /* optional [N][G][2] (sum, sumsq) accumulated over the written output       */
-    int gn_groups;        /* G for gn_stats                                                            */
+    double* gn_stats;     /* reserved, must be NULL (statistics come from pu_gn_stats; a per-channel    */
+    int gn_groups;        /* reduction in this row-per-lane epilogue costs more than that pass)         */
 } PuConvArgs;
 /* forward conv and, with a mode-1 packed weight, data gradient (convolution_backward's grad_input) */
 int pu_conv2d(const PuConvArgs* a, void* stream);

@@ -1007,12 +1007,12 @@ extern "C" int pu_conv2d(const PuConvArgs* a, void* stream) {
     PU_REQUIRE(a->ksize == 1 || a->ksize == 3, "pu_conv2d: ksize must be 1 or 3 (got %d)", a->ksize);
     PU_REQUIRE(a->dtype == PU_F32 || a->dtype == PU_BF16, "pu_conv2d: bad dtype %d", a->dtype);
     PU_REQUIRE(a->C1 == 0 || a->src1, "pu_conv2d: C1 > 0 needs src1");
+    PU_REQUIRE(!a->gn_stats, "pu_conv2d: gn_stats is reserved and must be NULL (use pu_gn_stats)");
     bool tc = pu::conv_tc_applicable(a) && !(a->flags & PU_CONV_FORCE_SIMPLE);
     if (a->flags & PU_CONV_FORCE_TC)
         PU_REQUIRE(tc, "pu_conv2d: PU_CONV_FORCE_TC but the tcgen05 kernel does not apply (dtype=%d C0=%d C1=%d Cout=%d)",
                    a->dtype, a->C0, a->C1, a->Cout);
     if (tc) return pu::conv_tc_launch(a, st);
-    PU_REQUIRE(!a->gn_stats, "pu_conv2d: gn_stats fusion needs the tcgen05 kernel");
     return pu::conv_simple_launch(a, st);
 }
 
