@@ -85,3 +85,47 @@ def test_two_gpu_gradients_equal_full_batch(tmp_path):
         # between the two runs (see test_model_gpu.py), hence the looser bound on the maximum
         assert errs[len(errs) // 2][0] <= 2e-5, (step, errs[-3:])
         assert errs[-1][0] <= 2e-2, (step, errs[-3:])
+
+
+def _ens_worker(rank, world, port, out_path):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    try:
+        from prob_unet_mds_b200 import parallel
+        m = _make_model(dev)
+        m.eval()
+        x, _ = synth.make_inputs(B, H, H, seed=1)
+        S = 6
+        g = torch.Generator().manual_seed(3)
+        eps = torch.randn(B, S, L, generator=g).to(dev)
+        out, (s_lo, s_hi) = parallel.ensemble_sharded(m, x.to(dev), S, eps=eps)
+        torch.save({'out': out.cpu(), 'range': (s_lo, s_hi)}, f'{out_path}.{rank}')
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+def test_two_gpu_sharded_ensemble_equals_single_process(tmp_path):
+    """SURVEY 8e, ensemble row: inputs sharded for the encode, features all-gathered, members sharded for the decode.
+    The two ranks' member blocks together must equal the single-process ensemble for the same eps."""
+    out_path = str(tmp_path / 'ens.pt')
+    mp.spawn(_ens_worker, args=(2, _free_port(), out_path), nprocs=2, join=True)
+    dev = torch.device('cuda', 0)
+    m = _make_model(dev)
+    m.eval()
+    x, _ = synth.make_inputs(B, H, H, seed=1)
+    S = 6
+    g = torch.Generator().manual_seed(3)
+    eps = torch.randn(B, S, L, generator=g).to(dev)
+    ref = m.sample_ensemble(x.to(dev), S, eps=eps).cpu()
+    covered = []
+    for rank in range(2):
+        blk = torch.load(f'{out_path}.{rank}')
+        lo, hi = blk['range']
+        covered += list(range(lo, hi))
+        assert blk['out'].shape == (B, hi - lo) + tuple(ref.shape[2:])
+        err = (blk['out'] - ref[:, lo:hi]).norm().item() / ref[:, lo:hi].norm().item()
+        assert err <= 1e-5, (rank, err)
+    assert covered == list(range(S))
