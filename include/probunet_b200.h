@@ -37,6 +37,12 @@ int pu_version(void);
 int pu_device_supports_tc(void);
 /* number of kernels launched by this library since the last reset (per process) */
 long long pu_launch_count(int reset);
+/* Stream-ordered zero fill of `bytes` bytes (cudaMemsetAsync): the loss / statistics accumulators and the zero-padded
+ * input channels that the host side would otherwise clear with torch.zeros (an ATen fill kernel). */
+int pu_zero(void* dst, long long bytes, void* stream);
+/* Stream-ordered device-to-device copy (cudaMemcpyAsync), e.g. the skip-conv bias gradient, which has the same values as
+ * conv1's bias gradient (networks.py:176-177: both biases are added to the same sum) but needs its own storage. */
+int pu_copy(void* dst, const void* src, long long bytes, void* stream);
 
 /* ---------------- layout / packing ---------------- */
 /* fp32 NCHW [N,C,H,W] -> NHWC dst[..., c_off : c_off+C] of a tensor with Cdst channels. Replaces the implicit

@@ -56,6 +56,8 @@ _SIGNATURES = {
     'pu_version': (c_int, []),
     'pu_device_supports_tc': (c_int, []),
     'pu_launch_count': (c_ll, [c_int]),
+    'pu_zero': (c_int, [c_void_p, c_ll, c_void_p]),
+    'pu_copy': (c_int, [c_void_p, c_void_p, c_ll, c_void_p]),
     'pu_nchw_to_nhwc': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'pu_nhwc_to_nchw': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'pu_pack_conv_weight': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_int, c_void_p]),

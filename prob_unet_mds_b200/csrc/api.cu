@@ -37,6 +37,16 @@ long long pu_launch_count(int reset) {
     if (reset) pu::g_launches.store(0);
     return v;
 }
+int pu_zero(void* dst, long long bytes, void* stream) {
+    PU_REQUIRE(dst != nullptr && bytes >= 0, "pu_zero: bad arguments");
+    PU_CUDA(cudaMemsetAsync(dst, 0, (size_t)bytes, (cudaStream_t)stream));
+    return PU_OK;
+}
+int pu_copy(void* dst, const void* src, long long bytes, void* stream) {
+    PU_REQUIRE(dst != nullptr && src != nullptr && bytes >= 0, "pu_copy: bad arguments");
+    PU_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return PU_OK;
+}
 int pu_device_supports_tc(void) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;

@@ -537,21 +537,13 @@ int attention_fwd_tc(const void* qkv, void* out, float* lse, int N, int T, int h
     CUtensorMap tm;
     int rc = make_mat_tmap(&tm, qkv, (long long)N * T, 3LL * C, 128);
     if (rc) return rc;
-    static bool attr = false;
-    if (!attr) {
-        PU_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-        attr = true;
-    }
+    PU_SMEM_ATTR(attn_fwd_tc_kernel, AT_SMEM);
     AttnFwdParams p;
     p.T = T; p.heads = heads; p.C = C;
     p.out = (__nv_bfloat16*)out;
     p.lse = lse;
     if (T % (2 * AT_TQ) == 0) {
-        static bool attr2 = false;
-        if (!attr2) {
-            PU_CUDA(cudaFuncSetAttribute(attn_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM));
-            attr2 = true;
-        }
+        PU_SMEM_ATTR(attn_fwd_tc2_kernel, A2_SMEM);
         dim3 grid2(T / (2 * AT_TQ), N * heads);
         attn_fwd_tc2_kernel<<<grid2, 384, A2_SMEM, st>>>(tm, p);
         return check_launch("attn_fwd_tc2");
@@ -1114,11 +1106,7 @@ int attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const 
     if (rc) return rc;
     rc = make_mat_tmap(&tmdo, dout, (long long)N * T, (long long)C, 128);
     if (rc) return rc;
-    static bool attr = false;
-    if (!attr) {
-        PU_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
-        attr = true;
-    }
+    PU_SMEM_ATTR(attn_bwd_tc_kernel, AB_SMEM);
     PU_CUDA(cudaMemsetAsync(dq_acc, 0, sizeof(float) * (size_t)N * T * C, st));
     AttnBwdParams p;
     p.T = T; p.heads = heads; p.C = C;
@@ -1129,11 +1117,7 @@ int attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const 
     if (ev && ev[0] == '1') {
         attn_bwd_tc_kernel<<<grid, 384, AB_SMEM, st>>>(tm, tmdo, p);
     } else {
-        static bool attr2 = false;
-        if (!attr2) {
-            PU_CUDA(cudaFuncSetAttribute(attn_bwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB2_SMEM));
-            attr2 = true;
-        }
+        PU_SMEM_ATTR(attn_bwd_tc2_kernel, AB2_SMEM);
         attn_bwd_tc2_kernel<<<grid, 384, AB2_SMEM, st>>>(tm, tmdo, p);
     }
     rc = check_launch("attn_bwd_tc");

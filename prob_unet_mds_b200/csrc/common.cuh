@@ -40,6 +40,20 @@ int check_launch(const char* what);
         }                                                                          \
     } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: set it once per (call site, device), so a process
+// that drives several GPUs (or several host threads) never launches a >48 KB kernel without it.
+#define PU_SMEM_ATTR(kernel, bytes)                                                                              \
+    do {                                                                                                         \
+        static unsigned long long done__ = 0ull; /* bit d = set on device d */                                   \
+        int dev__ = 0;                                                                                           \
+        PU_CUDA(cudaGetDevice(&dev__));                                                                          \
+        const unsigned long long bit__ = 1ull << (dev__ & 63);                                                   \
+        if (!(__atomic_load_n(&done__, __ATOMIC_ACQUIRE) & bit__)) {                                             \
+            PU_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));    \
+            __atomic_fetch_or(&done__, bit__, __ATOMIC_RELEASE);                                                 \
+        }                                                                                                        \
+    } while (0)
+
 __host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline long long cdivll(long long a, long long b) { return (a + b - 1) / b; }
 

@@ -859,11 +859,7 @@ static int conv_tc_launch_bn(const PuConvArgs* a, cudaStream_t st) {
     rc = make_mat_tmap(&tB, a->weight, a->Cout, (long long)a->ksize * a->ksize * (a->C0 + a->C1), BN);
     if (rc) return rc;
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        PU_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-        attr_set = true;
-    }
+    PU_SMEM_ATTR((conv_tc_kernel<BN, MT>), Cfg::SMEM);
     int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
     conv_tc_kernel<BN, MT><<<grid, 384, Cfg::SMEM, st>>>(tA0, tA1, tB, p);
     return check_launch("conv_tc");
@@ -947,22 +943,14 @@ static int wgrad_tc_launch_bn(const PuWgradArgs* a, cudaStream_t st) {
         tX1 = tX0;
     if (rc) return rc;
 
-    static bool attr_set = false;
     int grid = p.total_items < num_sms() ? p.total_items : num_sms();
     if constexpr (MODE == 0) {
         using Cfg = WgradTcCfg<BN>;
-        if (!attr_set) {
-            PU_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-            attr_set = true;
-        }
+        PU_SMEM_ATTR(wgrad_tc_kernel<BN>, Cfg::SMEM);
         wgrad_tc_kernel<BN><<<grid, 256, Cfg::SMEM, st>>>(tDY, tX0, tX1, p);
     } else {
         using Cfg = Wgrad2Cfg<BN, MODE>;
-        if (!attr_set) {
-            PU_CUDA(cudaFuncSetAttribute(wgrad_tc2_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM));
-            attr_set = true;
-        }
+        PU_SMEM_ATTR((wgrad_tc2_kernel<BN, MODE>), Cfg::SMEM);
         wgrad_tc2_kernel<BN, MODE><<<grid, 256, Cfg::SMEM, st>>>(tDY, tX0, tX1, p);
     }
     return check_launch("wgrad_tc");

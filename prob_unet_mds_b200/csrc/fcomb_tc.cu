@@ -219,12 +219,7 @@ bool fcomb_members_tc_applicable(const PuFcombArgs* a) {
 }
 
 int fcomb_members_tc_launch(const PuFcombArgs* a, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(fcomb_members_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM);
-        PU_REQUIRE(e == cudaSuccess, "fcomb_members_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-        attr_set = true;
-    }
+    PU_SMEM_ATTR(fcomb_members_tc_kernel, FT_SMEM);
     dim3 grid(a->HW / FT_ROWS, a->N, cdiv(a->S, FT_SCHUNK));
     fcomb_members_tc_kernel<<<grid, FT_THREADS, FT_SMEM, st>>>(*a);
     return check_launch("fcomb_members_tc");

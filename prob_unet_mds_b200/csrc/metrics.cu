@@ -58,11 +58,8 @@ extern "C" int pu_crps_empirical(const float* pred, const float* truth, float* o
     PU_REQUIRE(pred && truth && out && S >= 1 && outer > 0 && inner > 0, "pu_crps_empirical: bad arguments");
     const size_t smem = sizeof(float) * (size_t)S * CRPS_THREADS;
     PU_REQUIRE(smem <= 200 * 1024, "pu_crps_empirical: at most %d ensemble members (got %d)", 200 * 1024 / (4 * CRPS_THREADS), S);
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
-        PU_CUDA(cudaFuncSetAttribute(crps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
-    }
+    // per-device attribute and S varies from call to call: set it on every large call (a cheap driver call)
+    if (smem > 48 * 1024) PU_CUDA(cudaFuncSetAttribute(crps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long blocks = cdivll(outer * inner, CRPS_THREADS);
     PU_REQUIRE(blocks < (1LL << 31), "pu_crps_empirical: too many elements");
     crps_kernel<<<(unsigned)blocks, CRPS_THREADS, smem, (cudaStream_t)stream>>>(pred, truth, out, S, outer, inner, member_stride,

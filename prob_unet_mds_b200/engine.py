@@ -50,6 +50,9 @@ class _PackCache:
     def __init__(self):
         self._store = {}
 
+    def clear(self):
+        self._store.clear()
+
     def get(self, key, param, make):
         tag = (param._version, param.data_ptr())
         hit = self._store.get(key)
@@ -292,7 +295,7 @@ class UNetEngine:
         # skip branch
         rs = rec['rs']
         if blk.skip is not None and blk.skip.weight is not None:
-            grads[id(blk.skip.bias)] = bias_dy.clone()   # same values as conv1.bias' gradient, own storage
+            grads[id(blk.skip.bias)] = ops.clone(bias_dy)   # same values as conv1.bias' gradient, own storage
             dres = ops.conv2d(dy, self.w_dgrad(blk.skip.weight), Cin, 1)
             dres_rs = L.RS_NONE
             self._wgrad(grads, blk.skip.weight, xa, dy, 1, src1=xb)

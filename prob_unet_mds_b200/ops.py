@@ -16,13 +16,31 @@ def _nhwc(t):
     return t.shape
 
 
+def zeros(shape, dtype, device):
+    """torch.empty + a stream-ordered cudaMemsetAsync (pu_zero) -- no ATen fill kernel on the path."""
+    t = torch.empty(shape, dtype=dtype, device=device)
+    check(lib().pu_zero(ptr(t), t.numel() * t.element_size(), stream_ptr()), 'zero')
+    return t
+
+
+def clone(t):
+    assert t.is_contiguous()
+    out = torch.empty_like(t)
+    check(lib().pu_copy(ptr(out), ptr(t), t.numel() * t.element_size(), stream_ptr()), 'copy')
+    return out
+
+
+def zeros_f64(n, device):
+    return zeros((n,), torch.float64, device)
+
+
 # ----------------------------------------------------------------------------- layout / packing
 def nchw_to_nhwc(x, dtype, out=None, c_off=0, Cdst=None):
     N, Cc, H, W = x.shape
     assert x.dtype == torch.float32 and x.is_contiguous() and x.is_cuda
     if out is None:
         Cdst = Cdst or Cc
-        out = (torch.zeros if Cdst != Cc else torch.empty)((N, H, W, Cdst), dtype=dtype, device=x.device)
+        out = (zeros if Cdst != Cc else torch.empty)((N, H, W, Cdst), dtype=dtype, device=x.device)
     check(lib().pu_nchw_to_nhwc(ptr(x), ptr(out), N, Cc, H, W, out.shape[3], c_off, dtype_code(out.dtype), stream_ptr()),
           'nchw_to_nhwc')
     return out

@@ -83,6 +83,9 @@ class AdamW(torch.optim.Optimizer):
                     check(L.lib().pu_adamw_multi(tab.data_ptr(), len(idx), float(group['lr']), float(b1), float(b2),
                                                  float(group['eps']), float(group['weight_decay']), step, stream_ptr()),
                           'adamw_multi')
+                # the kernel wrote the parameters through raw pointers: tell autograd (and every cache keyed on
+                # param._version, e.g. engine._PackCache's packed conv weights) that they changed
+                torch.autograd.graph.increment_version(ps)
                 # keep the table and the (possibly re-laid-out) gradients alive until the kernel has been enqueued
                 self._keep = (host, tab, grads)
         return loss

@@ -36,7 +36,13 @@ class BucketedSink(GradSink):
         if slot is None:
             return torch.empty_like(p)
         b, off = slot
-        return self.owner.flat[b][off:off + p.numel()].view_as(p)
+        view = self.owner.flat[b][off:off + p.numel()].view_as(p)
+        if p.grad is not None and p.grad.data_ptr() == view.data_ptr():
+            # gradient accumulation (a second backward without zero_grad(set_to_none=True)): param.grad still IS the
+            # bucket view of the previous backward.  Move the old gradient out of the bucket so that this backward
+            # can overwrite the bucket, all-reduce it, and let autograd add it to the preserved old value.
+            p.grad = p.grad.clone()
+        return view
 
     def __setitem__(self, pid, g):
         super().__setitem__(pid, g)
@@ -73,8 +79,9 @@ class DataParallel:
     def broadcast_parameters(self):
         if self.world() == 1:
             return
-        for t in list(self.model.parameters()) + list(self.model.buffers()):
-            dist.broadcast(t.data, src=0, group=self.group)
+        with torch.no_grad():
+            for t in list(self.model.parameters()) + list(self.model.buffers()):
+                dist.broadcast(t, src=0, group=self.group)     # on the tensor itself: bumps its version counter
 
     def make_sink(self):
         return BucketedSink(self)
@@ -122,6 +129,9 @@ class DataParallel:
         b, off = slot
         view = self.flat[b][off:off + g.numel()]
         if g.data_ptr() != view.data_ptr():      # produced elsewhere (e.g. a cached zero gradient): stage it
+            p = self.by_id.get(pid)
+            if p is not None and p.grad is not None and p.grad.data_ptr() == view.data_ptr():
+                p.grad = p.grad.clone()          # gradient accumulation: see BucketedSink.alloc
             view.copy_(g.reshape(-1))
             dict.__setitem__(sink, pid, view.view_as(g))
         cnt = sink._pending.get(b, 0) + 1

@@ -191,6 +191,28 @@ class ProbabilisticUNet(nn.Module):
         self._check_flag()
         return out
 
+    # ---- sample() ------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def sample(self, x, num_samples=1, eps=None):
+        """BASELINE.json's north_star names a ``sample()`` method; the reference has none -- its sampling is
+        ``model(inputs, training=False)`` called num_samples times (train_prob_unet_model.py:176-182), i.e. z ~ prior(x)
+        decoded by Fcomb.  ``sample(x)`` returns one such draw [B, num_classes, H, W] (same result as
+        ``forward(x, training=False)`` for the same eps); ``sample(x, S)`` returns [B, S, num_classes, H, W] with the
+        U-Net and the prior evaluated once per input (``sample_ensemble``).  eps: optional [B, L] / [B, S, L]."""
+        if num_samples == 1 and (eps is None or eps.dim() == 2):
+            if eps is not None:
+                self.eps_override = eps
+            return self.forward(x, training=False)
+        return self.sample_ensemble(x, num_samples, eps=eps)
+
+    def invalidate_packed_weights(self):
+        """Drop the packed (bf16 / re-laid-out) copies of the conv weights.  They are refreshed automatically when a
+        parameter's version counter changes (optimizer steps, load_state_dict, in-place ops); call this after writing
+        parameters through ``.data`` or raw pointers, which bypass the version counter."""
+        for eng in (getattr(self.unet, '_engine', None), self.prior._engine, self.posterior._engine):
+            if eng is not None:
+                eng.cache.clear()
+
     # ---- ensemble sampling (SURVEY 3.3 / 8e: encode once, S x Fcomb) ---------------------------------------------------
     @torch.no_grad()
     def sample_ensemble(self, x, num_samples, eps=None):
@@ -221,9 +243,48 @@ class ProbabilisticUNet(nn.Module):
         self.unet.compute_dtype = self.compute_dtype
         named = self._named()
         params = [p for _, p in named]
-        total, recon, kl = _ElboFunction.apply(self, x, target, *params)
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            total, recon, kl = _ElboFunction.apply(self, x, target, *params)
+        else:       # evaluation (eval_probunet_model runs elbo under @torch.no_grad): no tape, no saved activations
+            total, recon, kl, _ = _elbo_forward(self, x, target, save=False)
         self._check_flag()
         return total, recon, kl
+
+
+def _elbo_forward(model, x, target, save):
+    """The forward half of elbo (prob_unet.py:214-232).  save=False (eval under torch.no_grad, as the reference's
+    eval_probunet_model does, train_prob_unet_model.py:109) keeps no backward tape and no Fcomb hidden activations."""
+    dt = model.compute_dtype
+    dev = x.device
+    B, _, H, W = x.shape
+    ue = model.unet.engine()
+    ue._step += 1
+    x = x.contiguous()
+    target = target.contiguous()
+    feat, utape = ue.forward(engine.input_nhwc(x, dt), model.unet.training, save, seed_base=engine._seed_base(ue._step))
+    pe, qe = model.prior.engine(dt), model.posterior.engine(dt)
+    mu_p, ls_p, ptape = pe.forward(model.prior._input(x, None, dt), save=save)
+    mu_q, ls_q, qtape = qe.forward(model.posterior._input(x, target, dt), save=save)
+    model._flag_for(dev)
+    eps = model._draw_eps(B, dev)
+    z, sigma_q = ops.rsample(mu_q, ls_q, eps, model._flag)
+    _, sigma_p = ops.rsample(mu_p, ls_p, eps, model._flag)
+    w0, b0, w1, b1, w2, b2 = [p.detach() for p in model.fcomb.params()]
+    out, h1, h2 = ops.fcomb_fwd(feat, z, w0, b0, w1, b1, w2, b2, save_hidden=save)
+    acc = ops.zeros_f64(2, dev)
+    ops.mse_fwd_bwd(out, target, acc[0:1])
+    ops.kl_fwd_bwd(mu_q, ls_q, mu_p, ls_p, acc[1:2], want_grads=False)
+    total, recon, kl = ops.loss_finalize(acc, model.beta)
+    # side-effect attributes of the reference (prob_unet.py:217-218)
+    model.prior_latent_space = model._dist(mu_p, sigma_p)
+    model.posterior_latent_space = model._dist(mu_q, sigma_q)
+    model.last_output = out
+    model.last_z = z
+    saved = None
+    if save:
+        saved = dict(utape=utape, ptape=ptape, qtape=qtape, feat=feat, z=z, eps=eps, sigma_q=sigma_q, out=out,
+                     h1=h1, h2=h2, target=target, mu_p=mu_p, ls_p=ls_p, mu_q=mu_q, ls_q=ls_q, HW=H * W)
+    return total, recon, kl, saved
 
 
 class _ElboFunction(torch.autograd.Function):
@@ -231,35 +292,9 @@ class _ElboFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, x, target, *params):
-        dt = model.compute_dtype
-        dev = x.device
-        B, _, H, W = x.shape
-        ue = model.unet.engine()
-        ue._step += 1
-        x = x.contiguous()
-        target = target.contiguous()
-        feat, utape = ue.forward(engine.input_nhwc(x, dt), model.unet.training, True, seed_base=engine._seed_base(ue._step))
-        pe, qe = model.prior.engine(dt), model.posterior.engine(dt)
-        mu_p, ls_p, ptape = pe.forward(model.prior._input(x, None, dt), save=True)
-        mu_q, ls_q, qtape = qe.forward(model.posterior._input(x, target, dt), save=True)
-        model._flag_for(dev)
-        eps = model._draw_eps(B, dev)
-        z, sigma_q = ops.rsample(mu_q, ls_q, eps, model._flag)
-        _, sigma_p = ops.rsample(mu_p, ls_p, eps, model._flag)
-        w0, b0, w1, b1, w2, b2 = [p.detach() for p in model.fcomb.params()]
-        out, h1, h2 = ops.fcomb_fwd(feat, z, w0, b0, w1, b1, w2, b2, save_hidden=True)
-        acc = torch.zeros(2, dtype=torch.float64, device=dev)
-        ops.mse_fwd_bwd(out, target, acc[0:1])
-        ops.kl_fwd_bwd(mu_q, ls_q, mu_p, ls_p, acc[1:2], want_grads=False)
-        total, recon, kl = ops.loss_finalize(acc, model.beta)
-        # side-effect attributes of the reference (prob_unet.py:217-218)
-        model.prior_latent_space = model._dist(mu_p, sigma_p)
-        model.posterior_latent_space = model._dist(mu_q, sigma_q)
-        model.last_output = out
-        model.last_z = z
+        total, recon, kl, saved = _elbo_forward(model, x, target, save=True)
         ctx.model = model
-        ctx.saved = dict(utape=utape, ptape=ptape, qtape=qtape, feat=feat, z=z, eps=eps, sigma_q=sigma_q, out=out,
-                         h1=h1, h2=h2, target=target, mu_p=mu_p, ls_p=ls_p, mu_q=mu_q, ls_q=ls_q, HW=H * W)
+        ctx.saved = saved
         return total, recon, kl
 
     @staticmethod
@@ -276,7 +311,7 @@ class _ElboFunction(torch.autograd.Function):
         Lz = model.latent_dim
         scales = ops.loss_bwd_scales(g_total, g_recon, g_kl, model.beta, dev)
         # reconstruction branch: d recon / d logits, then Fcomb backward (prob_unet.py:224-227)
-        scratch = torch.zeros(2, dtype=torch.float64, device=dev)
+        scratch = ops.zeros_f64(2, dev)
         dlogits = ops.mse_fwd_bwd(s['out'], s['target'], scratch[0:1], dtype=dt, gscale=scales[0:1])
         feat, h1, h2 = s['feat'], s['h1'], s['h2']
         # layer 2: 64 -> num_classes

@@ -74,6 +74,23 @@ def _worker(rank, world, port):
                 b, off = dp.slots[id(model.a)]
                 assert sink[id(model.a)].data_ptr() == dp.flat[b][off:].data_ptr()
         assert len(dp.flat) >= 2                       # 8 KiB buckets -> several buckets
+        # gradient accumulation: two backward passes without zero_grad(set_to_none=True).  param.grad of the first pass
+        # IS the bucket view; the second pass must not overwrite it before autograd's AccumulateGrad adds to it.
+        params = [model.d, model.c, model.b, model.a]
+        for p in params:
+            p.grad = None
+        for step in (5, 6):
+            sink = model._grad_sink_factory()
+            _fake_backward(model, sink, rank, step)
+            for p in params:                               # what AccumulateGrad does
+                g = sink[id(p)]
+                if p.grad is None:
+                    p.grad = g
+                else:
+                    p.grad.add_(g)
+        for k, p in enumerate(params):
+            want = sum(float(r + 1) * (k + 1) + 5 for r in range(world)) + sum(float(r + 1) * (k + 1) + 6 for r in range(world))
+            assert torch.allclose(p.grad, torch.full_like(p, want)), (k, p.grad.flatten()[:3], want)
         assert [id(p) for p in dp.order] == [id(model.d), id(model.c), id(model.b), id(model.a)]
         t, = parallel.allreduce_losses(torch.tensor(float(rank + 1)))
         assert t.item() == 3.0
