@@ -56,6 +56,9 @@ int pu_nhwc_to_nchw(const void* src, float* dst, int N, int C, int H, int W, int
 /* OIHW fp32 master weight -> packed weight in `dtype`.
  *   mode 0 (forward): dst[co'][ky][kx][ci]           = src[perm(co')][ci][ky][kx]
  *   mode 1 (dgrad)  : dst[ci][ky][kx][co']           = src[perm(co')][ci][k-1-ky][k-1-kx]
+ *   mode 2 (forward, bf16 hi/lo split): dst[co'][ky][kx][0..Ci_pad) = bf16(w), [Ci_pad..2*Ci_pad) = bf16(w - bf16(w));
+ *           used with pu_conv2d(src0 = x, src1 = x) so that (w_hi + w_lo) * x is accumulated: the prior / posterior
+ *           encoders (prob_unet.py:44-78) whose bf16 weight rounding would otherwise cost 1e-3..2e-3 of the KL term
  * ci is padded with zeros up to Ci_pad (mode 0) ; out_perm (device int32[Co]) may be NULL (identity).
  * Replaces `self.weight.to(x.dtype)` (networks.py:69).                                                           */
 int pu_pack_conv_weight(const float* src, void* dst, int Co, int Ci, int k, int Ci_pad, int mode,

@@ -57,6 +57,33 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, T* __restrict_
     }
 }
 
+// mode 2: forward packing with the bf16 rounding error of every weight kept as a second K block per tap:
+//   dst[co][tap][0 .. Ci_pad)        = bf16(w)
+//   dst[co][tap][Ci_pad .. 2 Ci_pad) = bf16(w - float(bf16(w)))
+// A convolution over the channel concatenation [x ; x] with this weight computes (w_hi + w_lo) * x, i.e. the weights
+// enter with ~16 mantissa bits instead of 8 while the kernel, its operands and its accumulation stay what they are.
+__global__ void pack_weight_split_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int Co, int Ci,
+                                         int k, int Ci_pad, const int* __restrict__ perm, long long src_co_stride) {
+    const int kk = k * k;
+    long long total = (long long)Co * kk * Ci_pad;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int ci = (int)(i % Ci_pad);
+        long long t = i / Ci_pad;
+        int tap = (int)(t % kk);
+        int co = (int)(t / kk);
+        float v = 0.f;
+        if (ci < Ci) {
+            int sco = perm ? perm[co] : co;
+            v = src[(long long)sco * src_co_stride + (long long)ci * kk + tap];
+        }
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        __nv_bfloat16* d = dst + ((long long)co * kk + tap) * 2 * Ci_pad + ci;
+        d[0] = hi;
+        d[Ci_pad] = lo;
+    }
+}
+
 __global__ void unpack_wgrad_kernel(const float* __restrict__ src, float* __restrict__ dst, int Co, int Ci, int k,
                                     int Ci_pad, const int* __restrict__ perm, int accumulate, long long dst_co_stride) {
     const int kk = k * k;
@@ -146,11 +173,17 @@ int pu_nhwc_to_nchw(const void* src, float* dst, int N, int C, int H, int W, int
 
 int pu_pack_conv_weight(const float* src, void* dst, int Co, int Ci, int k, int Ci_pad, int mode, const int* out_perm,
                         long long src_co_stride, int dtype, void* stream) {
-    PU_REQUIRE(src && dst && Co > 0 && Ci > 0 && (k == 1 || k == 3) && Ci_pad >= Ci && (mode == 0 || mode == 1),
+    PU_REQUIRE(src && dst && Co > 0 && Ci > 0 && (k == 1 || k == 3) && Ci_pad >= Ci && mode >= 0 && mode <= 2,
                "pu_pack_conv_weight: bad arguments");
-    PU_REQUIRE(mode == 0 || Ci_pad == Ci, "pu_pack_conv_weight: dgrad packing takes no channel padding");
+    PU_REQUIRE(mode != 1 || Ci_pad == Ci, "pu_pack_conv_weight: dgrad packing takes no channel padding");
+    PU_REQUIRE(mode != 2 || dtype == PU_BF16, "pu_pack_conv_weight: the hi/lo split packing (mode 2) is bf16 only");
     cudaStream_t st = (cudaStream_t)stream;
     if (src_co_stride <= 0) src_co_stride = (long long)Ci * k * k;
+    if (mode == 2) {
+        pu::pack_weight_split_kernel<<<pu::grid_for((long long)Co * k * k * Ci_pad), 256, 0, st>>>(
+            src, (__nv_bfloat16*)dst, Co, Ci, k, Ci_pad, out_perm, src_co_stride);
+        return pu::check_launch("pack_conv_weight");
+    }
     long long total = (mode == 0) ? (long long)Co * k * k * Ci_pad : (long long)Ci * k * k * Co;
     if (dtype == PU_F32)
         pu::pack_weight_kernel<float><<<pu::grid_for(total), 256, 0, st>>>(src, (float*)dst, Co, Ci, k, Ci_pad, mode,

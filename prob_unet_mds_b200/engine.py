@@ -406,8 +406,12 @@ class GaussianEngine:
         self.cache = _PackCache()
 
     def w_fwd(self, p, Ci_pad=None):
-        return self.cache.get((id(p), 'f', self.dtype, Ci_pad), p,
-                              lambda: ops.pack_weight(p.detach(), 0, self.dtype, Ci_pad=Ci_pad))
+        # bf16 mode: hi/lo split packing (pu_pack_conv_weight mode 2).  The KL term is a function of mu_q - mu_p, and
+        # the bf16 rounding of the encoder WEIGHTS alone moves it by 1e-3..2e-3 (activations: 5e-5); the split keeps the
+        # tcgen05 kernel and doubles K of these forward convs (<1 % of the step's FLOPs).
+        mode = 2 if self.dtype == torch.bfloat16 else 0
+        return self.cache.get((id(p), 'f', self.dtype, Ci_pad, mode), p,
+                              lambda: ops.pack_weight(p.detach(), mode, self.dtype, Ci_pad=Ci_pad))
 
     def w_dgrad(self, p):
         return self.cache.get((id(p), 'd', self.dtype), p, lambda: ops.pack_weight(p.detach(), 1, self.dtype))
@@ -421,7 +425,9 @@ class GaussianEngine:
         x = xin
         acts = []
         for i, c in enumerate(convs):
-            r = ops.conv2d(x, self.w_fwd(c.weight, Ci_pad=x.shape[3]), c.out_channels, 3, bias=c.bias, relu=True)
+            split = self.dtype == torch.bfloat16
+            r = ops.conv2d(x, self.w_fwd(c.weight, Ci_pad=x.shape[3]), c.out_channels, 3, bias=c.bias, relu=True,
+                           src1=x if split else None)
             last = i == len(convs) - 1
             acts.append((x, r))
             if not last:

@@ -59,7 +59,7 @@ def pack_weight(w, mode, dtype, Ci_pad=None, perm=None, Ci=None, src_co_stride=0
     k = w.shape[-1] if w.dim() == 4 else 1
     Ci = Ci if Ci is not None else w.shape[1]
     Ci_pad = Ci_pad or Ci
-    shape = (Co, k, k, Ci_pad) if mode == 0 else (Ci, k, k, Co)
+    shape = (Co, k, k, Ci_pad) if mode == 0 else ((Ci, k, k, Co) if mode == 1 else (Co, k, k, 2 * Ci_pad))
     if out is None:
         out = torch.empty(shape, dtype=dtype, device=w.device)
     check(lib().pu_pack_conv_weight(ptr(w), ptr(out), Co, Ci, k, Ci_pad, mode, ptr(perm), src_co_stride,

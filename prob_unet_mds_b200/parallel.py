@@ -11,6 +11,8 @@ fp32 buckets laid out in backward order; as soon as the last gradient of a bucke
 all-reduced on a side stream while the main stream keeps running the backward kernels.  There is no copy in or out
 of the buckets: the views are what autograd stores in `param.grad`.
 """
+import contextlib
+
 import torch
 import torch.distributed as dist
 
@@ -69,6 +71,9 @@ class DataParallel:
         self._works = []
         self._stream = None
         self.by_id = {id(p): p for p in model.parameters()}
+        self._sync = True        # False inside no_sync(): gradients stay local (gradient accumulation micro-steps)
+        self._local_acc = False  # param.grad currently holds un-reduced gradients of no_sync micro-steps
+        self.bucket_params = None
         model._grad_sink_factory = self.make_sink
         self.broadcast_parameters()
 
@@ -84,7 +89,34 @@ class DataParallel:
                 dist.broadcast(t, src=0, group=self.group)     # on the tensor itself: bumps its version counter
 
     def make_sink(self):
+        if not self._sync:
+            self._local_acc = True
+            return GradSink()        # plain tensors, no communication; autograd accumulates them into param.grad
         return BucketedSink(self)
+
+    @contextlib.contextmanager
+    def no_sync(self):
+        """Gradient accumulation (a global batch larger than world x per-GPU micro-batch, BASELINE.json configs[2] on
+        fewer than 8 GPUs): backward passes inside the context leave their gradients local in ``param.grad``; the
+        first backward outside it folds them into the all-reduce buckets, so the exchanged gradient is the SUM over all
+        micro-batches of all ranks.  Start every accumulation window with ``zero_grad(set_to_none=True)``."""
+        prev, self._sync = self._sync, False
+        try:
+            yield
+        finally:
+            self._sync = prev
+
+    def _fold_local(self, b):
+        """Adds the locally accumulated (un-reduced) gradients of bucket b's parameters into the bucket and clears
+        them, so that autograd stores the reduced bucket view as param.grad afterwards."""
+        views, olds = [], []
+        for p, off in self.bucket_params[b]:
+            if p.grad is not None:
+                views.append(self.flat[b][off:off + p.numel()].view_as(p))
+                olds.append(p.grad)
+                p.grad = None
+        if views:
+            torch._foreach_add_(views, olds)
 
     def slot_of(self, p):
         return None if self.slots is None else self.slots.get(id(p))
@@ -94,7 +126,7 @@ class DataParallel:
             self.order.append(p)
 
     def _build_buckets(self):
-        self.slots, self.flat, self.bucket_members = {}, [], []
+        self.slots, self.flat, self.bucket_members, self.bucket_params = {}, [], [], []
         cur, size = [], 0
         groups = []
         for p in self.order:
@@ -109,10 +141,13 @@ class DataParallel:
             n = sum(((p.numel() + 3) // 4) * 4 for p in ps)   # keep every view 16-byte aligned
             self.flat.append(torch.zeros(n, dtype=torch.float32, device=ps[0].device))
             off = 0
+            members = []
             for p in ps:
                 self.slots[id(p)] = (b, off)
+                members.append((p, off))
                 off += ((p.numel() + 3) // 4) * 4
             self.bucket_members.append(len(ps))
+            self.bucket_params.append(members)
 
     # -- per-step protocol --------------------------------------------------------------------------------------------
     def ready(self, pid, g, sink):
@@ -137,6 +172,8 @@ class DataParallel:
         cnt = sink._pending.get(b, 0) + 1
         sink._pending[b] = cnt
         if cnt == self.bucket_members[b]:
+            if self._local_acc:
+                self._fold_local(b)
             self._launch(self.flat[b])
 
     def _launch(self, flat):
@@ -154,16 +191,23 @@ class DataParallel:
             if self.slots is None:
                 # first step: order just learned; reduce everything now, bucketed from the next step on
                 for pid, g in list(sink.items()):
+                    p = self.by_id.get(pid)
+                    if self._local_acc and p is not None and p.grad is not None:
+                        g.add_(p.grad)
+                        p.grad = None
                     dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
             else:
                 for b, members in enumerate(self.bucket_members):
                     if sink._pending.get(b, 0) != members and sink._pending.get(b, 0) > 0:
+                        if self._local_acc:
+                            self._fold_local(b)
                         self._launch(self.flat[b])     # partially filled (some grads legitimately absent)
                 for w in self._works:
                     w.wait()
                 self._works = []
                 if self._stream is not None:
                     torch.cuda.current_stream().wait_stream(self._stream)
+        self._local_acc = False
         if self.slots is None and self.order:
             self._build_buckets()
 

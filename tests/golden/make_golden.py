@@ -53,6 +53,26 @@ def disable_dropout(model):
             m.dropout = 0
 
 
+def _autocast_bf16(model, x, t, seed):
+    """The reference's OWN bf16 behaviour: the unmodified model under torch.autocast(bfloat16) on the CPU, same weights,
+    same inputs, same eps.  Its distance from the fp32 run is the noise floor that a bf16 pipeline is measured against
+    (tests/test_model_gpu.py: the product's bf16 logits error must not exceed the reference's own autocast error).
+    Under autocast mu is bf16, and torch's CPU normal_() produces a different stream for bf16 tensors than for fp32
+    ones, so the fp32 draw of the same seed is injected through torch.distributions' _standard_normal hook."""
+    import torch.distributions.normal as tdn
+    torch.manual_seed(seed)
+    eps32 = torch.empty([x.shape[0], model.latent_dim]).normal_()
+    orig = tdn._standard_normal
+    tdn._standard_normal = lambda shape, dtype, device: eps32.to(dtype)
+    try:
+        with torch.no_grad(), torch.autocast('cpu', dtype=torch.bfloat16):
+            total, recon, kl = model.elbo(x, t)
+            y = model(x, t, training=True)
+    finally:
+        tdn._standard_normal = orig
+    return dict(ac_total=float(total), ac_recon=float(recon), ac_kl=float(kl), ac_post_output=y.float().numpy())
+
+
 def probunet_case(tag, B, H, L, grads=True):
     sys.path.insert(0, REF)
     from prob_unet import ProbabilisticUNet
@@ -100,6 +120,18 @@ def probunet_case(tag, B, H, L, grads=True):
     torch.manual_seed(78)
     out['post_eps'] = torch.empty([B, L]).normal_().numpy()
     out['post_output'] = y2.numpy()
+    # noise floor of bf16 arithmetic, measured on the reference itself (posterior-branch logits for post_eps, losses)
+    out.update(_autocast_bf16(model, x, t, 78))
+    d = out['ac_post_output'].astype(np.float64) - out['post_output'].astype(np.float64)
+    out['ac_post_output_relerr'] = float(np.linalg.norm(d) / np.linalg.norm(out['post_output'].astype(np.float64)))
+    del out['ac_post_output']          # only its error is needed; keeps the fixture small
+    with torch.no_grad():
+        torch.manual_seed(78)
+        tot78, rec78, kl78 = model.elbo(x, t)
+    out['ac_total_relerr'] = abs(out['ac_total'] - float(tot78)) / abs(float(tot78))
+    out['ac_kl_relerr'] = abs(out['ac_kl'] - float(kl78)) / abs(float(kl78))
+    print(tag, 'reference under CPU autocast(bf16): logits rel err', out['ac_post_output_relerr'], 'ELBO rel err',
+          out['ac_total_relerr'], 'KL rel err', out['ac_kl_relerr'])
     np.savez_compressed(os.path.join(HERE, f'{tag}.npz'), **out)
     print(tag, 'total', out['total'], 'recon', out['recon'], 'kl', out['kl'])
 
@@ -127,5 +159,5 @@ if __name__ == '__main__':
     torch.set_num_threads(8)
     probunet_case('probunet_32_L6_B2', 2, 32, 6)
     probunet_case('probunet_64_L16_B1', 1, 64, 16)
-    probunet_case('probunet_128_L16_B1', 1, 128, 16, grads=False)
+    probunet_case('probunet_128_L16_B1', 1, 128, 16)
     detunet_case('detunet_64_B1', 1, 64)

@@ -57,8 +57,11 @@ def make_weights(schema, seed=0):
             # the residual branches end in conv1/proj: keep them a bit smaller so 29 blocks stay O(1)
             if key.endswith(('conv1.weight', 'proj.weight')):
                 gain = 0.5
-            # prior/posterior heads: make log_sigma modest and mu spread so that KL is O(1..100)
+            # prior/posterior heads: spread mu so that KL is O(10) (5.6 at 32x32/L6, 12.7 at 64x64/L16 -- SURVEY section 4
+            # item 5: a KL of 0.3 is a difference of nearly equal numbers and tests little); log_sigma stays modest
+            if 'conv_mu' in key:
+                gain = 8.0
             if 'conv_log_sigma' in key:
-                gain = 0.3
+                gain = 1.0
             sd[key] = torch.randn(shape, generator=g) * (gain / math.sqrt(fan_in))
     return sd

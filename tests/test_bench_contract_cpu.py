@@ -9,7 +9,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_the_contract_line():
     env = dict(os.environ, OMP_NUM_THREADS='1')      # what torchrun exports; the arm must still use the host's cores
-    r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1'],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1',
+                        '--cpu-batch', '1'],     # bounded for the CPU suite; the default is configs[0]'s batch 8
                        capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith('{')]
@@ -22,7 +23,8 @@ def test_reference_arm_prints_the_contract_line():
     assert d['higher_is_better'] is True and d['vs_baseline'] is None and d['data'] == 'synthetic'
     assert 'workload' in d['config'] and 'model' not in d['config']
     cb = d['cpu_baseline']
-    assert cb['kind'] == 'port' and cb['value'] == d['value'] and cb['cores'] == (os.cpu_count() or 1) and cb['sample']
+    staged = os.path.exists(os.path.join(ROOT, 'oracle', '_ref', 'prob_unet.py'))
+    assert cb['kind'] == ('reference' if staged else 'port') and cb['value'] == d['value'] and cb['cores'] == (os.cpu_count() or 1) and cb['sample']
     assert d['e2e'] == {'value': d['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
 
 

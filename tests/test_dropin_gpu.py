@@ -79,3 +79,49 @@ def test_module_alias_and_reference_loops():
     model2.load_state_dict(sd)
     for k, v in model2.state_dict().items():
         assert torch.equal(v, sd[k])
+
+
+def test_unmodified_reference_loops_drive_the_b200_model():
+    """The reference's own train_prob_unet_model.py (staged byte for byte under oracle/_ref by oracle/make_ref.py; absent
+    -> skipped) is imported UNMODIFIED and its train_probunet_step / eval_probunet_model / sample_probunet_model run
+    against the B200 model.  Only wandb (not installed; logging only, wandb_active=False) is stubbed."""
+    import importlib
+    import os
+    import types
+    from oracle import make_ref
+    if not make_ref.available():
+        pytest.skip('oracle/_ref is not staged (python oracle/make_ref.py needs /root/reference)')
+    sys.modules.setdefault('wandb', types.ModuleType('wandb'))
+    if make_ref.REF_DST not in sys.path:
+        sys.path.insert(0, make_ref.REF_DST)
+    tm = importlib.import_module('train_prob_unet_model')
+    assert os.path.dirname(os.path.abspath(tm.__file__)) == make_ref.REF_DST
+    from prob_unet_mds_b200 import ProbabilisticUNet
+
+    class _Set(_Synthetic):
+        # the extra batch keys and the two dataset methods sample_probunet_model uses (climex_utils.py:156-164, :198-211, :364)
+        def __getitem__(self, i):
+            d = super().__getitem__(i)
+            d.update(lrinterp=self.x[i], hr=self.x[i] + self.t[i], stand_stats=torch.zeros(1))
+            return d
+
+        def residual_to_hr(self, residual, lrinterp, stand_stats=None):
+            return lrinterp + residual
+
+        def plot_sample_batch(self, *a, **k):
+            self.plotted = True
+            return None, None
+
+    torch.manual_seed(0)
+    model = ProbabilisticUNet(input_channels=3, num_classes=3, latent_dim=6, num_filters=[64, 128, 256, 512]).to(DEV)
+    model.load_state_dict(synth.make_weights(synth.load_schema('schema_probunet_L6.json'), seed=0))
+    ds = _Set(8, 32)
+    loader = DataLoader(ds, batch_size=4, shuffle=False, num_workers=0)
+    optimizer = torch.optim.AdamW(model.parameters(), lr=1e-4)
+    means = [tm.train_probunet_step(model, loader, optimizer, epoch, 3, 1, False, DEV) for epoch in range(3)]
+    assert all(m == m for m in means) and means[-1] < means[0]          # finite, and it trains
+    val = tm.eval_probunet_model(model, loader, False, DEV)
+    assert val == val and val > 0
+    hr_preds, _ = tm.sample_probunet_model(model, loader, 0, DEV)
+    assert hr_preds.shape == (2, 3, 3, 32, 32) and ds.plotted
+    assert not torch.equal(hr_preds[:, 0], hr_preds[:, 1])              # different latent draws

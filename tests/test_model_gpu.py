@@ -2,6 +2,13 @@
 
 Tolerances (BASELINE.json north_star): logits / KL / ELBO within 1e-3 relative in bf16 (fp32 accumulation),
 1e-5 in fp32 mode; z bit-exact for the same eps.
+
+bf16 LOGITS: 1e-3 on a whole tensor is below what bf16 storage allows (one rounding is 1.1e-3 RMS).  The floor is
+pinned by the reference ITSELF: tests/golden/make_golden.py runs the unmodified reference under
+torch.autocast(bfloat16) and stores its logits error against its own fp32 run (`ac_post_output_relerr`: 1.4e-2 at
+32x32, 5.7e-3 at 64x64, 5.6e-3 at 128x128; its KL is off by 1.4e-3..4.5e-3).  The product's bf16 logits must be at
+least as close to the fp32 reference as the reference's own bf16 run is (_bf16_logits_floor); ELBO / recon / KL keep
+the stated 1e-3.
 """
 import os
 
@@ -91,6 +98,11 @@ def _select_subgradient(named, sd, x, t, eps, ref, ref_grads, tau=1e-5, max_unit
     return g, chosen
 
 
+def _bf16_logits_floor(fx):
+    """Error of the reference's own bf16-autocast logits against its fp32 logits (make_golden._autocast_bf16)."""
+    return float(fx['ac_post_output_relerr'])
+
+
 def _rel(a, b):
     return (a.double() - b.double()).norm().item() / (b.double().norm().item() + 1e-30)
 
@@ -117,7 +129,7 @@ def test_elbo_and_grads_match_oracle_32(precision):
     assert abs(total.item() - ref['total'].item()) <= tol * abs(ref['total'].item())
     logits_err = _rel(m.last_output.cpu(), ref['output'].detach())
     print(f'[{precision}] logits rel err {logits_err:.3e}')
-    assert logits_err <= (2e-5 if precision == 'fp32' else 2e-2)
+    assert logits_err <= (2e-5 if precision == 'fp32' else _bf16_logits_floor(fx)), (logits_err, _bf16_logits_floor(fx))
     # z is bit-exact given the same (mu, sigma, eps)
     q = m.posterior_latent_space.base_dist
     assert torch.equal(m.last_z, q.loc + eps.to(DEV) * q.scale)
@@ -186,13 +198,67 @@ def test_golden_losses_and_sampling(tag, B, H, L, precision):
     y = m(x, training=False)
     err = _rel(y.cpu(), torch.from_numpy(fx['sample_output']))
     print(f'[{tag} {precision}] sample rel err {err:.3e}')
-    assert err <= (3e-5 if precision == 'fp32' else 2e-2)
+    assert err <= (3e-5 if precision == 'fp32' else _bf16_logits_floor(fx)), (err, _bf16_logits_floor(fx))
     p = m.prior_latent_space.base_dist
     assert torch.equal(m.last_z, p.loc + torch.from_numpy(fx['sample_eps']).to(DEV) * p.scale)
     # posterior branch: forward(x, target, training=True)
     m.eps_override = torch.from_numpy(fx['post_eps'])
     y2 = m(x, t, training=True)
-    assert _rel(y2.cpu(), torch.from_numpy(fx['post_output'])) <= (3e-5 if precision == 'fp32' else 2e-2)
+    err2 = _rel(y2.cpu(), torch.from_numpy(fx['post_output']))
+    print(f'[{tag} {precision}] posterior-branch logits rel err {err2:.3e} (reference under bf16 autocast: '
+          f'{_bf16_logits_floor(fx):.3e})')
+    assert err2 <= (3e-5 if precision == 'fp32' else _bf16_logits_floor(fx)), (err2, _bf16_logits_floor(fx))
+    # north_star's sample(): one prior draw == forward(training=False) for the same eps
+    m.eps_override = None
+    y3 = m.sample(x, eps=torch.from_numpy(fx['sample_eps']))
+    assert _rel(y3.cpu(), torch.from_numpy(fx['sample_output'])) <= (3e-5 if precision == 'fp32' else _bf16_logits_floor(fx))
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+@pytest.mark.parametrize('tag,H,L', [('probunet_64_L16_B1', 64, 16), ('probunet_128_L16_B1', 128, 16)])
+def test_elbo_and_grads_match_oracle_tensor_core_levels(tag, H, L, precision):
+    """64x64 and 128x128 inputs: every U-Net level is at least one tensor-core tile wide (128x128: 128/64/32/16 pixels),
+    attention runs at T = 4096 / 1024 / 256, so in bf16 mode the tcgen05 conv forward / dgrad, the halo weight-gradient
+    kernel and the tcgen05 attention forward / backward are what produce these gradients.  Compared tensor by tensor
+    with the fp64 oracle and with the digest of the reference's own gradients in the golden fixture."""
+    fx = np.load(os.path.join(G, tag + '.npz'))
+    m, sd = _model(L, precision)
+    m.train()
+    x, t = synth.make_inputs(1, H, H, seed=1)
+    eps = torch.from_numpy(fx['eps'])
+    m.eps_override = eps
+    total, recon, kl = m.elbo(x.to(DEV), t.to(DEV))
+    total.backward()
+    tol = 1e-5 if precision == 'fp32' else 1e-3
+    for name, got in (('total', total), ('recon', recon), ('kl', kl)):
+        want = float(fx[name])
+        assert abs(got.item() - want) <= max(tol, 3e-5 if name == 'kl' else 0) * abs(want) + 1e-6, (name, got.item(), want)
+    ref, ref_grads = _oracle_grads(sd, x, t, eps, record=True)
+    named = dict(m.named_parameters())
+    worst = _grad_errs(named, ref_grads)
+    median = worst[len(worst) // 2][0]
+    if precision == 'fp32' and (median > 2e-5 or worst[0][0] > 1e-4):
+        sel_grads, chosen = _select_subgradient(named, sd, x, t, eps, ref, ref_grads)
+        worst = _grad_errs(named, sel_grads)
+        median = worst[len(worst) // 2][0]
+    print(f'[{tag} {precision}] grad rel errs vs fp64 oracle: median {median:.3e}, worst:', worst[:5])
+    assert median <= (2e-5 if precision == 'fp32' else 5e-2), (median, worst[:5])
+    assert worst[0][0] <= (1e-4 if precision == 'fp32' else 1.5e-1), worst[:5]
+    # the reference's own (fp32 CPU) gradients: norm and six sampled elements of every tensor
+    names = [str(n) for n in fx['grad_names']]
+    assert set(names) == {k for k, p in named.items() if p.grad is not None}
+    bad = []
+    for name, row in zip(names, fx['grad_digest']):
+        g = named[name].grad.reshape(-1).double().cpu()
+        if abs(g.norm().item() - row[0]) > (1.5e-2 if precision == 'fp32' else 5e-2) * row[0] + 1e-9:
+            bad.append((name, g.norm().item(), row[0]))
+        if precision == 'fp32':
+            idx = grad_digest_indices(name, g.numel())
+            got = g[idx]
+            want = torch.tensor(row[3:])
+            if (got - want).abs().max().item() > 2e-2 * row[0] / max(1.0, g.numel()) ** 0.5 + 5e-3 * want.abs().max().item():
+                bad.append((name, 'elements', got.tolist(), want.tolist()))
+    assert not bad, bad[:5]
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'bf16'])
@@ -267,6 +333,68 @@ def test_training_steps_follow_oracle_trajectory():
         opt.step()
         print(f'step {step}: {total.item():.5f} vs oracle {r["total"].item():.5f}')
         assert abs(total.item() - r['total'].item()) <= 2e-4 * abs(r['total'].item())
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_package_adamw_refreshes_packed_weights(precision):
+    """The fused AdamW writes the parameters through raw pointers; the engines cache packed (bf16, re-laid-out) copies of
+    the conv weights keyed on the parameters' version counters, so the optimizer must bump them.  Two steps with the
+    package optimizer must track the same two steps with torch.optim.AdamW, and the loss must move."""
+    from prob_unet_mds_b200 import AdamW
+    L, B, H = 6, 2, 32
+    x, t = synth.make_inputs(B, H, H, seed=1)
+    x, t = x.to(DEV), t.to(DEV)
+    losses = {}
+    for which in ('ours', 'torch'):
+        m, _ = _model(L, precision)
+        m.train()
+        opt = AdamW(m.parameters(), lr=1e-3) if which == 'ours' else torch.optim.AdamW(m.parameters(), lr=1e-3)
+        vals = []
+        for step in range(3):
+            opt.zero_grad(set_to_none=True)
+            m.eps_override = synth.make_eps(B, L, seed=100 + step)
+            total, _, _ = m.elbo(x, t)
+            total.backward()
+            opt.step()
+            vals.append(total.item())
+        losses[which] = vals
+    print(precision, losses)
+    assert abs(losses['ours'][1] - losses['ours'][0]) > 1e-3 * abs(losses['ours'][0])     # the update took effect
+    for i, (a, b) in enumerate(zip(losses['ours'], losses['torch'])):
+        if precision == 'fp32':
+            assert abs(a - b) <= 2e-4 * abs(b), losses
+        else:
+            # the first Adam step is lr * sign(g) wherever |g| >> eps: bf16 noise on small gradient entries flips signs,
+            # so two bf16 trajectories (even two runs of the same optimizer) part by a fraction of the loss CHANGE
+            assert abs(a - b) <= 0.3 * abs(losses['torch'][i] - losses['torch'][0]) + 5e-4 * abs(b), losses
+
+
+def test_elbo_under_no_grad_keeps_no_tape():
+    """eval_probunet_model (train_prob_unet_model.py:109) calls elbo under @torch.no_grad: same numbers, no autograd
+    node, and no saved activations (the peak memory of the call stays far below the training forward's)."""
+    m, _ = _model(6, 'bf16')
+    m.eval()
+    x, t = synth.make_inputs(8, 64, 64, seed=1)
+    x, t = x.to(DEV), t.to(DEV)
+    eps = synth.make_eps(8, 6, seed=3)
+    m.eps_override = eps
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    with torch.no_grad():
+        a = m.elbo(x, t)
+    torch.cuda.synchronize()
+    peak_eval = torch.cuda.max_memory_allocated() - base
+    assert all(not v.requires_grad and v.grad_fn is None for v in a)
+    m.eps_override = eps
+    torch.cuda.reset_peak_memory_stats()
+    b = m.elbo(x, t)
+    torch.cuda.synchronize()
+    peak_train = torch.cuda.max_memory_allocated() - base
+    assert b[0].grad_fn is not None
+    assert abs(a[0].item() - b[0].item()) <= 1e-4 * abs(b[0].item())
+    print(f'peak memory: no_grad {peak_eval / 2**20:.0f} MiB, with tape {peak_train / 2**20:.0f} MiB')
+    assert peak_eval < 0.5 * peak_train
 
 
 def test_dropout_training_mode_runs_and_is_seeded():

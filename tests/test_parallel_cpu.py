@@ -92,6 +92,25 @@ def _worker(rank, world, port):
             want = sum(float(r + 1) * (k + 1) + 5 for r in range(world)) + sum(float(r + 1) * (k + 1) + 6 for r in range(world))
             assert torch.allclose(p.grad, torch.full_like(p, want)), (k, p.grad.flatten()[:3], want)
         assert [id(p) for p in dp.order] == [id(model.d), id(model.c), id(model.b), id(model.a)]
+        # no_sync(): micro-batches whose gradients stay local, folded into the all-reduce of the next synchronised step
+        for p in params:
+            p.grad = None
+        with dp.no_sync():
+            for step in (7, 8):
+                sink = model._grad_sink_factory()
+                assert type(sink) is parallel.GradSink
+                _fake_backward(model, sink, rank, step)
+                for p in params:
+                    g = sink[id(p)]
+                    p.grad = g if p.grad is None else p.grad.add_(g)
+        sink = model._grad_sink_factory()
+        _fake_backward(model, sink, rank, 9)
+        for p in params:
+            g = sink[id(p)]
+            p.grad = g if p.grad is None else p.grad.add_(g)
+        for k, p in enumerate(params):
+            want = sum(float(r + 1) * (k + 1) + st for r in range(world) for st in (7, 8, 9))
+            assert torch.allclose(p.grad, torch.full_like(p, want)), ('no_sync', k, p.grad.flatten()[:3], want)
         t, = parallel.allreduce_losses(torch.tensor(float(rank + 1)))
         assert t.item() == 3.0
     finally:
