@@ -86,8 +86,13 @@ typedef struct PuConvArgs {
     const float* bias;    /* fp32 or NULL (networks.py:88-89 x.add_(b))                                */
     const void* residual; /* NHWC [N,H,W,Cout] added in the epilogue or NULL (networks.py:176,183)     */
     void* out;            /* NHWC [N,H,W,Cout]; may alias residual                                     */
-    double* gn_stats;     /* reserved, must be NULL (statistics come from pu_gn_stats; a per-channel    */
-    int gn_groups;        /* reduction in this row-per-lane epilogue costs more than that pass)         */
+    double* qstats;       /* optional [N][Cout/4][2] fp64 (Cout % 4 == 0): receives (sum, sum of squares) of the */
+                          /* STORED output over the pixels of sample n, per quad of 4 consecutive channels --    */
+                          /* the GroupNorm statistics of the consumer (networks.py:104) taken in the producing   */
+                          /* conv's epilogue instead of a separate pass; zeroed by the call.  Groups of any size  */
+                          /* that is a multiple of 4, also over a channel concatenation of two such tensors, are  */
+                          /* formed from the quads by pu_gn_stats_from_quads                                      */
+    int reserved;         /* must be 0                                                                            */
 } PuConvArgs;
 /* forward conv and, with a mode-1 packed weight, data gradient (convolution_backward's grad_input) */
 int pu_conv2d(const PuConvArgs* a, void* stream);
@@ -110,6 +115,9 @@ int pu_bias_grad(const void* dy, float* db, long long pixels, int C, int dtype, 
 /* stats[n][g] = (sum, sumsq) in fp64 over the group's channels of src0||src1 (F.group_norm, networks.py:104) */
 int pu_gn_stats(const void* src0, const void* src1, int C0, int C1, int N, int HW, int G, int dtype,
                 double* stats, void* stream);
+/* stats[n][g] = sum of the quad statistics (PuConvArgs.qstats) of the group's channels; q1 / C1 describe the second
+ * source of a channel concatenation (NULL / 0: single source); (C0 + C1) / G must be a multiple of 4 */
+int pu_gn_stats_from_quads(const double* q0, const double* q1, int C0, int C1, int N, int G, double* stats, void* stream);
 typedef struct PuGnArgs {
     int N, H, W;          /* spatial size of the normalised tensor x                                   */
     int C0, C1, G;

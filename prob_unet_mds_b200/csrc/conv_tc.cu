@@ -118,9 +118,25 @@ struct ConvTcParams {
     const float* bias;
     const __nv_bfloat16* residual;
     __nv_bfloat16* out;
-    double* gn_stats;
-    int gn_groups;
+    double* qstats;         // [N][Cout/4][2] or nullptr
 };
+
+// Sums each of 16 per-lane values over the 32 lanes of the warp with 16 shuffles (recursive halving: at every step a
+// lane keeps one half of its values and hands the other half to its partner).  Returns the warp total of v[lane >> 1].
+__device__ __forceinline__ float warp_reduce_scatter16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int h = 8; h >= 1; h >>= 1) {
+        const int bit = 2 * h;                     // 16, 8, 4, 2
+        const bool up = (lane & bit) != 0;
+#pragma unroll
+        for (int i = 0; i < h; ++i) {
+            const float send = up ? v[i] : v[i + h];
+            const float keep = up ? v[i + h] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
 
 constexpr int TILE_W = 16, TILE_H = 8;      // 128 output pixels per CTA tile
 constexpr int A_BYTES = 128 * 128;          // 128 rows x 64 bf16
@@ -322,6 +338,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
                         for (int e = 0; e < 16; ++e) ov[e] = f[j + e];
                         st16(op + j, ov);
+                    }
+                }
+                if (p.qstats) {
+                    // GroupNorm statistics of the consumer, from the values as stored (bf16-rounded): per lane (= pixel)
+                    // the sum and sum of squares of each quad of channels, reduce-scattered over the 32 lanes (16
+                    // shuffles), then one fp64 atomic per lane pair into qstats[img][quad][2]
+                    float sv[16];
+#pragma unroll
+                    for (int qd = 0; qd < 8; ++qd) {
+                        float s = 0.f, ss = 0.f;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float rv = valid ? __bfloat162float(__float2bfloat16_rn(f[qd * 4 + e])) : 0.f;
+                            s += rv;
+                            ss = fmaf(rv, rv, ss);
+                        }
+                        sv[2 * qd] = s;
+                        sv[2 * qd + 1] = ss;
+                    }
+                    const float tot = warp_reduce_scatter16(sv, lane);      // total of sv[lane >> 1] over the warp
+                    if ((lane & 1) == 0) {
+                        const int idx = lane >> 1;                           // quad = idx >> 1, kind = idx & 1
+                        atomicAdd(p.qstats + ((long long)img * (p.Cout >> 2) + ((n0 + c) >> 2)) * 2 + idx, (double)tot);
                     }
                 }
             }
@@ -822,7 +861,6 @@ bool conv_tc_applicable(const PuConvArgs* a) {
     if (a->ksize != 1 && a->ksize != 3) return false;
     if (a->C0 <= 0 || a->C0 % 64 || a->C1 % 64 || a->Cout % 64) return false;
     if (a->W < TILE_W || a->H < TILE_H) return false;   // tiny test images: CUDA-core kernel
-    if (a->gn_stats) return false;
     return true;
 }
 
@@ -845,8 +883,7 @@ static int conv_tc_launch_bn(const PuConvArgs* a, cudaStream_t st) {
     p.bias = a->bias;
     p.residual = (const __nv_bfloat16*)a->residual;
     p.out = (__nv_bfloat16*)a->out;
-    p.gn_stats = a->gn_stats;
-    p.gn_groups = a->gn_groups;
+    p.qstats = a->qstats;
 
     CUtensorMap tA0, tA1, tB;
     int rc = make_act_tmap(&tA0, a->src0, a->N, a->H, a->W, a->C0, TILE_W, TILE_H);
@@ -995,13 +1032,19 @@ extern "C" int pu_conv2d(const PuConvArgs* a, void* stream) {
     PU_REQUIRE(a->ksize == 1 || a->ksize == 3, "pu_conv2d: ksize must be 1 or 3 (got %d)", a->ksize);
     PU_REQUIRE(a->dtype == PU_F32 || a->dtype == PU_BF16, "pu_conv2d: bad dtype %d", a->dtype);
     PU_REQUIRE(a->C1 == 0 || a->src1, "pu_conv2d: C1 > 0 needs src1");
-    PU_REQUIRE(!a->gn_stats, "pu_conv2d: gn_stats is reserved and must be NULL (use pu_gn_stats)");
+    PU_REQUIRE(a->reserved == 0, "pu_conv2d: reserved must be 0");
+    PU_REQUIRE(!a->qstats || a->Cout % 4 == 0, "pu_conv2d: qstats needs Cout %% 4 == 0 (got %d)", a->Cout);
     bool tc = pu::conv_tc_applicable(a) && !(a->flags & PU_CONV_FORCE_SIMPLE);
     if (a->flags & PU_CONV_FORCE_TC)
         PU_REQUIRE(tc, "pu_conv2d: PU_CONV_FORCE_TC but the tcgen05 kernel does not apply (dtype=%d C0=%d C1=%d Cout=%d)",
                    a->dtype, a->C0, a->C1, a->Cout);
+    if (a->qstats) PU_CUDA(cudaMemsetAsync(a->qstats, 0, sizeof(double) * 2 * (size_t)a->N * (a->Cout / 4), st));
     if (tc) return pu::conv_tc_launch(a, st);
-    return pu::conv_simple_launch(a, st);
+    pu::note_fallback("pu_conv2d", a->dtype, a->C0, a->C1, a->Cout, a->H, a->W);
+    int rc = pu::conv_simple_launch(a, st);
+    if (rc || !a->qstats) return rc;
+    // CUDA-core path (fp32 mode, images smaller than a tensor-core tile): the statistics come from a separate pass
+    return pu::gn_quad_stats_launch(a->out, a->dtype, a->N, a->H * a->W, a->Cout, a->qstats, st);
 }
 
 extern "C" int pu_conv2d_wgrad(const PuWgradArgs* a, void* stream) {
@@ -1015,5 +1058,6 @@ extern "C" int pu_conv2d_wgrad(const PuWgradArgs* a, void* stream) {
     bool tc = pu::wgrad_tc_applicable(a) && !(a->flags & PU_CONV_FORCE_SIMPLE);
     if (a->flags & PU_CONV_FORCE_TC) PU_REQUIRE(tc, "pu_conv2d_wgrad: PU_CONV_FORCE_TC but tcgen05 kernel does not apply");
     if (tc) return pu::wgrad_tc_launch(a, st);
+    pu::note_fallback("pu_conv2d_wgrad", a->dtype, a->C0, a->C1, a->Cout, a->H, a->W);
     return pu::wgrad_simple_launch(a, st);
 }
