@@ -63,6 +63,19 @@ int pu_nhwc_to_nchw(const void* src, float* dst, int N, int C, int H, int W, int
  * Replaces `self.weight.to(x.dtype)` (networks.py:69).                                                           */
 int pu_pack_conv_weight(const float* src, void* dst, int Co, int Ci, int k, int Ci_pad, int mode,
                         const int* out_perm, long long src_co_stride /* 0: Ci*k*k */, int dtype, void* stream);
+/* The same packing for MANY weights in one launch (the refresh of every packed copy after an optimizer step, SURVEY
+ * 8f-1): `items` is a DEVICE array; item i owns the 32x32 (co, ci) tiles [tile_begin, next item's tile_begin), i.e.
+ * ceil(Co/32) * ceil(Ci_pad/32) of them; total_tiles is their sum.  Field meanings as in pu_pack_conv_weight. */
+typedef struct PuPackItem {
+    const float* src;
+    void* dst;
+    const int* perm;          /* or NULL */
+    long long src_co_stride;  /* elements; Ci*k*k for a plain OIHW tensor */
+    int Co, Ci, k, Ci_pad;
+    int mode, dtype;
+    int tile_begin, pad_;
+} PuPackItem;
+int pu_pack_conv_weights_multi(const PuPackItem* items, int n_items, int total_tiles, void* stream);
 /* packed fp32 weight gradient [Co'][k][k][Ci_pad] -> OIHW fp32 .grad, dst = (accumulate ? dst : 0) + src */
 int pu_unpack_conv_wgrad(const float* src, float* dst, int Co, int Ci, int k, int Ci_pad, const int* out_perm,
                          long long dst_co_stride /* 0: Ci*k*k */, int accumulate, void* stream);

@@ -21,7 +21,7 @@ class PuConvArgs(C.Structure):
     _fields_ = [('N', c_int), ('H', c_int), ('W', c_int), ('C0', c_int), ('C1', c_int), ('Cout', c_int),
                 ('ksize', c_int), ('dtype', c_int), ('flags', c_int), ('bias_per_sample', c_int),
                 ('src0', c_void_p), ('src1', c_void_p), ('weight', c_void_p), ('bias', c_void_p),
-                ('residual', c_void_p), ('out', c_void_p), ('gn_stats', c_void_p), ('gn_groups', c_int)]
+                ('residual', c_void_p), ('out', c_void_p), ('qstats', c_void_p), ('reserved', c_int)]
 
 
 class PuWgradArgs(C.Structure):
@@ -61,6 +61,7 @@ _SIGNATURES = {
     'pu_nchw_to_nhwc': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'pu_nhwc_to_nchw': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'pu_pack_conv_weight': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_int, c_void_p]),
+    'pu_pack_conv_weights_multi': (c_int, [c_void_p, c_int, c_int, c_void_p]),
     'pu_unpack_conv_wgrad': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_int, c_void_p]),
     'pu_gather_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     'pu_scatter_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
@@ -68,6 +69,7 @@ _SIGNATURES = {
     'pu_conv2d_wgrad': (c_int, [C.POINTER(PuWgradArgs), c_void_p]),
     'pu_bias_grad': (c_int, [c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_void_p]),
     'pu_gn_stats': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'pu_gn_stats_from_quads': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'pu_gn_apply': (c_int, [C.POINTER(PuGnArgs), c_void_p]),
     'pu_gn_bwd': (c_int, [C.POINTER(PuGnBwdArgs), c_void_p]),
     'pu_attention_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),

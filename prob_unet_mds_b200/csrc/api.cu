@@ -1,10 +1,15 @@
 // Error plumbing, version and launch accounting of the C ABI (include/probunet_b200.h).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
+#include <mutex>
+#include <set>
+#include <tuple>
 
 #include "../../include/probunet_b200.h"
 #include "common.cuh"
+#include "conv_internal.h"
 
 namespace pu {
 static thread_local char g_err[512] = "";
@@ -26,6 +31,21 @@ int check_launch(const char* what) {
         return PU_ERR_CUDA;
     }
     return PU_OK;
+}
+void note_fallback(const char* what, int dtype, int C0, int C1, int Cout, int H, int W) {
+    if (dtype != PU_BF16) return;                       // fp32 mode runs on the CUDA-core kernels by design
+    if (C0 + C1 < 16 || Cout < 16) return;              // 3-channel heads (Fcomb logits and their gradients): by design too
+    static const bool quiet = getenv("PU_QUIET_FALLBACK") != nullptr;
+    if (quiet) return;
+    static std::mutex mu;
+    static std::set<std::tuple<int, int, int, int, int, bool>> seen;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!seen.insert(std::make_tuple(C0, C1, Cout, H, W, what[9] == '_')).second) return;
+    fprintf(stderr,
+            "probunet_b200: %s falls back to the CUDA-core kernel for C0=%d C1=%d Cout=%d at %dx%d (tcgen05 tiles need "
+            "channel counts that are multiples of 64 and images of at least 8x16 pixels); expect it to be ~100x slower "
+            "per FLOP [reported once per shape; PU_QUIET_FALLBACK=1 silences this]\n",
+            what, C0, C1, Cout, H, W);
 }
 }  // namespace pu
 

@@ -23,6 +23,7 @@
 #include <stdlib.h>
 
 #include <mutex>
+#include <unordered_map>
 
 #include "../../include/probunet_b200.h"
 #include "common.cuh"
@@ -53,8 +54,43 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
+// Descriptor cache ("cached TMA descriptors keyed by (ptr, shape)").  A tensor map is a pure function of
+// (base pointer, extents, box); PyTorch's caching allocator hands the same blocks back step after step, so in steady state
+// every launch finds its three maps here instead of paying three cuTensorMapEncodeTiled driver calls.  The cache holds
+// no reference to the memory: a stale entry for a freed-and-reallocated pointer encodes exactly the same bytes.
+struct TmapKey {
+    const void* ptr;
+    long long a, b;     // packed extents / box
+    bool operator==(const TmapKey& o) const { return ptr == o.ptr && a == o.a && b == o.b; }
+};
+struct TmapKeyHash {
+    size_t operator()(const TmapKey& k) const {
+        size_t h = std::hash<const void*>()(k.ptr);
+        h ^= std::hash<long long>()(k.a) + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
+        h ^= std::hash<long long>()(k.b) + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
+        return h;
+    }
+};
+static std::mutex g_tmap_mu;
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmaps;
+static bool tmap_lookup(const TmapKey& k, CUtensorMap* m) {
+    std::lock_guard<std::mutex> lock(g_tmap_mu);
+    auto it = g_tmaps.find(k);
+    if (it == g_tmaps.end()) return false;
+    *m = it->second;
+    return true;
+}
+static void tmap_store(const TmapKey& k, const CUtensorMap& m) {
+    std::lock_guard<std::mutex> lock(g_tmap_mu);
+    if (g_tmaps.size() > 16384) g_tmaps.clear();      // bounded: shapes and pointers of a training loop are few
+    g_tmaps[k] = m;
+}
+
 // NHWC bf16 activation [N][H][W][C] -> 4-D map, box {64, bw, bh, 1}, 128B swizzle, zero OOB fill
 int make_act_tmap(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int bw, int bh) {
+    const TmapKey key{ptr, ((long long)N << 40) | ((long long)H << 20) | (long long)W,
+                      ((long long)C << 24) | ((long long)bw << 12) | (long long)bh | (1LL << 62)};
+    if (tmap_lookup(key, m)) return PU_OK;
     EncodeTiledFn enc = get_encode();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled entry point not available");
@@ -71,11 +107,14 @@ int make_act_tmap(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, i
         set_error("cuTensorMapEncodeTiled(activation N=%d H=%d W=%d C=%d) failed: %d", N, H, W, C, (int)r);
         return PU_ERR_CUDA;
     }
+    tmap_store(key, *m);
     return PU_OK;
 }
 
 // row-major bf16 matrix [rows][cols] -> 2-D map, box {64, brows}
 int make_mat_tmap(CUtensorMap* m, const void* ptr, long long rows, long long cols, int brows) {
+    const TmapKey key{ptr, rows, (cols << 12) | (long long)brows};
+    if (tmap_lookup(key, m)) return PU_OK;
     EncodeTiledFn enc = get_encode();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled entry point not available");
@@ -92,6 +131,7 @@ int make_mat_tmap(CUtensorMap* m, const void* ptr, long long rows, long long col
         set_error("cuTensorMapEncodeTiled(matrix %lld x %lld) failed: %d", rows, cols, (int)r);
         return PU_ERR_CUDA;
     }
+    tmap_store(key, *m);
     return PU_OK;
 }
 

@@ -9,6 +9,7 @@
 // 4B read (reduce pass) + 4..6B read + 2B write (apply pass).
 #include "../../include/probunet_b200.h"
 #include "common.cuh"
+#include "conv_internal.h"
 
 namespace pu {
 
@@ -197,6 +198,57 @@ gn_stats_kernel(const T* __restrict__ s0, const T* __restrict__ s1, int C0, int 
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(stats + (long long)n * G * 2 + i, (double)sm[i]);
+}
+
+// ---- statistics per quad of channels (the layout conv_tc_kernel's epilogue produces), CUDA-core fallback ----
+template <typename T>
+__global__ void __launch_bounds__(GN_THREADS)
+gn_quad_stats_kernel(const T* __restrict__ x, int HW, int C, int rows, double* __restrict__ q) {
+    const int nq = C / 4, n = blockIdx.y;
+    const int r0 = blockIdx.x * rows;
+    const int r1 = min(HW, r0 + rows);
+    for (int qd = threadIdx.x; qd < nq; qd += blockDim.x) {        // consecutive threads: consecutive quads (coalesced)
+        float s = 0.f, ss = 0.f;
+        for (int r = r0; r < r1; ++r) {
+            const T* p = x + ((long long)n * HW + r) * C + qd * 4;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float v = ldf(p + e);
+                s += v;
+                ss = fmaf(v, v, ss);
+            }
+        }
+        atomicAdd(q + ((long long)n * nq + qd) * 2, (double)s);
+        atomicAdd(q + ((long long)n * nq + qd) * 2 + 1, (double)ss);
+    }
+}
+
+int gn_quad_stats_launch(const void* x, int dtype, int N, int HW, int C, double* q, cudaStream_t st) {
+    const int rows = 32;
+    dim3 grid(cdiv(HW, rows), N);
+    if (dtype == PU_F32)
+        gn_quad_stats_kernel<float><<<grid, GN_THREADS, 0, st>>>((const float*)x, HW, C, rows, q);
+    else
+        gn_quad_stats_kernel<__nv_bfloat16><<<grid, GN_THREADS, 0, st>>>((const __nv_bfloat16*)x, HW, C, rows, q);
+    return check_launch("gn_quad_stats");
+}
+
+// stats[n][g] = sum over the group's quads (of src0's table, then src1's) -- a few thousand numbers
+__global__ void gn_stats_from_quads_kernel(const double* __restrict__ q0, const double* __restrict__ q1, int C0, int C1,
+                                           int N, int G, double* __restrict__ stats) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * G) return;
+    const int n = i / G, g = i - n * G;
+    const int Cg = (C0 + C1) / G;
+    double s = 0.0, ss = 0.0;
+    for (int c = g * Cg; c < (g + 1) * Cg; c += 4) {
+        const double* p = (c < C0) ? q0 + ((long long)n * (C0 / 4) + c / 4) * 2
+                                   : q1 + ((long long)n * (C1 / 4) + (c - C0) / 4) * 2;
+        s += p[0];
+        ss += p[1];
+    }
+    stats[2 * i] = s;
+    stats[2 * i + 1] = ss;
 }
 
 // ---- forward apply ----
@@ -750,6 +802,16 @@ int pu_gn_stats(const void* src0, const void* src1, int C0, int C1, int N, int H
                                                                        (const __nv_bfloat16*)src1, C0, C1, HW, G, rows,
                                                                        stats);
     return check_launch("gn_stats");
+}
+
+int pu_gn_stats_from_quads(const double* q0, const double* q1, int C0, int C1, int N, int G, double* stats, void* stream) {
+    using namespace pu;
+    PU_REQUIRE(q0 && stats && N > 0 && G > 0 && C0 > 0 && C1 >= 0, "pu_gn_stats_from_quads: bad arguments");
+    PU_REQUIRE(C1 == 0 || q1, "pu_gn_stats_from_quads: C1 > 0 needs q1");
+    PU_REQUIRE(C0 % 4 == 0 && C1 % 4 == 0 && (C0 + C1) % G == 0 && ((C0 + C1) / G) % 4 == 0,
+               "pu_gn_stats_from_quads: channels (%d,%d) / groups %d must give group sizes that are multiples of 4", C0, C1, G);
+    gn_stats_from_quads_kernel<<<cdiv(N * G, 128), 128, 0, (cudaStream_t)stream>>>(q0, q1, C0, C1, N, G, stats);
+    return check_launch("gn_stats_from_quads");
 }
 
 int pu_gn_apply(const PuGnArgs* a, void* stream) {

@@ -84,6 +84,70 @@ __global__ void pack_weight_split_kernel(const float* __restrict__ src, __nv_bfl
     }
 }
 
+// ---- multi-tensor packing: every conv weight of a model in ONE launch (after each optimizer step) ----
+// One block per (item, 32 output channels, 32 input channels) tile: the tile's [32][32*k*k] fp32 source rows are read
+// with coalesced loads into shared memory and written back as contiguous runs of the destination layout (32 input
+// channels for the forward / split packing, 32 output channels for the data-gradient packing).
+__device__ __forceinline__ void pack_store(void* dst, long long i, float v, int dtype) {
+    if (dtype == PU_F32)
+        reinterpret_cast<float*>(dst)[i] = v;
+    else
+        reinterpret_cast<__nv_bfloat16*>(dst)[i] = __float2bfloat16_rn(v);
+}
+
+__global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PuPackItem* __restrict__ items, int n_items) {
+    __shared__ float t[32][32 * 9 + 1];
+    // binary search: last item with tile_begin <= blockIdx.x
+    int lo = 0, hi = n_items - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (items[mid].tile_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    const PuPackItem it = items[lo];
+    const int kk = it.k * it.k;
+    const int ci_tiles = (it.Ci_pad + 31) / 32;
+    const int tile = blockIdx.x - it.tile_begin;
+    const int co0 = (tile / ci_tiles) * 32, ci0 = (tile % ci_tiles) * 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int ncol = it.Ci - ci0;                 // real input channels in this tile (<= 0: padding only)
+    ncol = ncol > 32 ? 32 : (ncol < 0 ? 0 : ncol);
+    for (int r = warp; r < 32; r += 8) {
+        const int co = co0 + r;
+        if (co < it.Co) {
+            const int sco = it.perm ? it.perm[co] : co;
+            const float* s = it.src + (long long)sco * it.src_co_stride + (long long)ci0 * kk;
+            for (int j = lane; j < 32 * kk; j += 32) t[r][j] = j < ncol * kk ? s[j] : 0.f;
+        }
+    }
+    __syncthreads();
+    if (it.mode != 1) {
+        const int cstride = it.mode == 2 ? 2 * it.Ci_pad : it.Ci_pad;
+        const int ci = ci0 + lane;
+        for (int rt = warp; rt < 32 * kk; rt += 8) {
+            const int r = rt / kk, tap = rt - r * kk;
+            const int co = co0 + r;
+            if (co >= it.Co || ci >= it.Ci_pad) continue;
+            const float v = t[r][lane * kk + tap];
+            const long long o = ((long long)co * kk + tap) * cstride + ci;
+            if (it.mode == 2) {
+                const __nv_bfloat16 h = __float2bfloat16_rn(v);
+                reinterpret_cast<__nv_bfloat16*>(it.dst)[o] = h;
+                reinterpret_cast<__nv_bfloat16*>(it.dst)[o + it.Ci_pad] = __float2bfloat16_rn(v - __bfloat162float(h));
+            } else {
+                pack_store(it.dst, o, v, it.dtype);
+            }
+        }
+    } else {
+        const int co = co0 + lane;
+        for (int ct = warp; ct < 32 * kk; ct += 8) {
+            const int c = ct / kk, tap = ct - c * kk;
+            const int ci = ci0 + c;
+            if (ci >= it.Ci || co >= it.Co) continue;
+            pack_store(it.dst, ((long long)ci * kk + (kk - 1 - tap)) * it.Co + co, t[lane][c * kk + tap], it.dtype);
+        }
+    }
+}
+
 __global__ void unpack_wgrad_kernel(const float* __restrict__ src, float* __restrict__ dst, int Co, int Ci, int k,
                                     int Ci_pad, const int* __restrict__ perm, int accumulate, long long dst_co_stride) {
     const int kk = k * k;
@@ -192,6 +256,12 @@ int pu_pack_conv_weight(const float* src, void* dst, int Co, int Ci, int k, int 
         pu::pack_weight_kernel<__nv_bfloat16><<<pu::grid_for(total), 256, 0, st>>>(src, (__nv_bfloat16*)dst, Co, Ci, k,
                                                                                  Ci_pad, mode, out_perm, src_co_stride);
     return pu::check_launch("pack_conv_weight");
+}
+
+int pu_pack_conv_weights_multi(const PuPackItem* items, int n_items, int total_tiles, void* stream) {
+    PU_REQUIRE(items && n_items > 0 && total_tiles > 0, "pu_pack_conv_weights_multi: bad arguments");
+    pu::pack_weights_multi_kernel<<<total_tiles, 256, 0, (cudaStream_t)stream>>>(items, n_items);
+    return pu::check_launch("pack_conv_weights_multi");
 }
 
 int pu_unpack_conv_wgrad(const float* src, float* dst, int Co, int Ci, int k, int Ci_pad, const int* out_perm,

@@ -9,6 +9,7 @@ are re-packed from the fp32 OIHW master parameters into [Cout][kh][kw][Cin] (for
 (flipped, data-gradient) whenever a parameter's version counter changes; parameter gradients are fp32.
 """
 import os
+import weakref
 
 import torch
 
@@ -45,22 +46,63 @@ def _require_cuda(t, what):
 
 
 class _PackCache:
-    """Packed copies of parameters, refreshed when the parameter is modified in place (optimizer step) or moved."""
+    """Packed copies of parameters, refreshed when the parameter is modified in place (optimizer step) or moved.
+
+    Conv weights are registered with their packing spec: the first use packs them one by one; afterwards
+    ``refresh()`` (called at the start of every forward) re-packs ALL stale ones in place with a single
+    pu_pack_conv_weights_multi launch -- stable buffers (the TMA descriptor cache keeps hitting) and one launch per
+    engine and step instead of one per weight and layout."""
 
     def __init__(self):
-        self._store = {}
+        self._store = {}      # key -> (tag, value)
+        self._specs = {}      # key -> (param, dict(mode, perm, Ci_pad)) for conv weights
+        self._table = None    # (signature, device table, n_items, total_tiles)
 
     def clear(self):
         self._store.clear()
+        self._specs.clear()
+        self._table = None
+
+    @staticmethod
+    def _tag(param):
+        return (param._version, param.data_ptr())
 
     def get(self, key, param, make):
-        tag = (param._version, param.data_ptr())
+        tag = self._tag(param)
         hit = self._store.get(key)
         if hit is not None and hit[0] == tag:
             return hit[1]
         val = make()
         self._store[key] = (tag, val)
         return val
+
+    def get_weight(self, key, param, dtype, mode, perm=None, Ci_pad=None):
+        tag = self._tag(param)
+        hit = self._store.get(key)
+        if hit is not None and hit[0] == tag:
+            return hit[1]
+        val = ops.pack_weight(param.detach(), mode, dtype, perm=perm, Ci_pad=Ci_pad,
+                              out=hit[1] if hit is not None else None)
+        self._store[key] = (tag, val)
+        self._specs[key] = (param, dict(mode=mode, perm=perm, Ci_pad=Ci_pad, dtype=dtype))
+        return val
+
+    def refresh(self):
+        """Re-pack every registered conv weight whose parameter changed since it was packed: one launch."""
+        stale = [k for k, (p, _) in self._specs.items() if self._store[k][0] != self._tag(p)]
+        if not stale:
+            return
+        sig = tuple((k, self._specs[k][0].data_ptr(), self._store[k][1].data_ptr()) for k in stale)
+        if self._table is None or self._table[0] != sig:
+            items = []
+            for k in stale:
+                p, spec = self._specs[k]
+                items.append(ops.pack_item(p.detach(), self._store[k][1], **spec))
+            self._table = (sig,) + ops.pack_table(items, self._specs[stale[0]][0].device)
+        _, table, n_items, total_tiles = self._table
+        ops.pack_weights_multi(table, n_items, total_tiles)
+        for k in stale:
+            self._store[k] = (self._tag(self._specs[k][0]), self._store[k][1])
 
 
 # ======================================================================================================================
@@ -76,11 +118,10 @@ class UNetEngine:
 
     # ---- packed parameters ------------------------------------------------------------------------------------------
     def w_fwd(self, p, perm=None, Ci_pad=None):
-        return self.cache.get((id(p), 'f', self.dtype, Ci_pad), p,
-                              lambda: ops.pack_weight(p.detach(), 0, self.dtype, perm=perm, Ci_pad=Ci_pad))
+        return self.cache.get_weight((id(p), 'f', self.dtype, Ci_pad), p, self.dtype, 0, perm=perm, Ci_pad=Ci_pad)
 
     def w_dgrad(self, p, perm=None):
-        return self.cache.get((id(p), 'd', self.dtype), p, lambda: ops.pack_weight(p.detach(), 1, self.dtype, perm=perm))
+        return self.cache.get_weight((id(p), 'd', self.dtype), p, self.dtype, 1, perm=perm)
 
     def qkv_perm(self, C, heads, device):
         """my channel (j, head, d) -> reference channel head*192 + d*3 + j  (networks.py:180 reshape/unbind)."""
@@ -104,6 +145,11 @@ class UNetEngine:
         tape = [] if save else None
         skips = []
         bi = 0
+        # GroupNorm statistics come out of the producing convolutions' epilogues (per quad of channels); self._q maps an
+        # activation tensor to them for its consumers (the next block's norm0, also across a skip concatenation)
+        self._q = {}
+        self._fused_stats = os.environ.get('PROBUNET_B200_FUSED_GN_STATS', '1') != '0'
+        self.cache.refresh()
         for name, mod in u.enc.items():
             if isinstance(mod, torch.nn.Module) and hasattr(mod, 'norm0'):
                 x, rec = self._block_fwd(mod, x, None, training, seed_base + bi, save)
@@ -111,8 +157,8 @@ class UNetEngine:
             else:
                 xin = x
                 # xin may carry zero channels up to a multiple of 64 (input_nhwc) so that the tcgen05 kernel applies
-                x = ops.conv2d(xin, self.w_fwd(mod.weight, Ci_pad=xin.shape[3]), mod.out_channels, mod.kernel,
-                               bias=mod.bias)
+                x = self._conv_q(xin, self.w_fwd(mod.weight, Ci_pad=xin.shape[3]), mod.out_channels, mod.kernel,
+                                 bias=mod.bias)
                 rec = dict(kind='conv', mod=mod, xin=xin, out=x)
             if save:
                 tape.append(rec)
@@ -125,20 +171,39 @@ class UNetEngine:
             bi += 1
             if save:
                 tape.append(rec)
-        st = ops.gn_stats(x)
+        st = self._stats(x)
         h = ops.gn_apply(x, st, u.out_norm.weight, u.out_norm.bias, silu=True, eps=u.out_norm.eps)
         feat = ops.conv2d(h, self.w_fwd(u.out_conv.weight), u.out_conv.out_channels, 3, bias=u.out_conv.bias)
         if save:
             tape.append(dict(kind='out', x=x, st=st, h=h, out=feat))
+        self._q = {}
         return feat, tape
+
+    def _conv_q(self, *args, **kw):
+        """conv2d whose output feeds a GroupNorm: its epilogue also emits the per-quad (sum, sumsq)."""
+        if not self._fused_stats:
+            return ops.conv2d(*args, **kw)
+        y, q = ops.conv2d(*args, want_qstats=True, **kw)
+        self._q[id(y)] = (weakref.ref(y), q)     # weak: the table must not keep activations alive in eval mode
+        return y
+
+    def _quads(self, x):
+        ent = self._q.get(id(x)) if x is not None else None
+        return ent[1] if ent is not None and ent[0]() is x else None
+
+    def _stats(self, xa, xb=None):
+        qa, qb = self._quads(xa), self._quads(xb)
+        if qa is None or (xb is not None and qb is None):
+            return ops.gn_stats(xa, xb)
+        return ops.gn_stats_from_quads(qa, qb)
 
     def _block_fwd(self, blk, xa, xb, training, seed, save):
         Cout = blk.out_channels
         rs = L.RS_UP if blk.up else (L.RS_DOWN if blk.down else L.RS_NONE)
-        st0 = ops.gn_stats(xa, xb)
+        st0 = self._stats(xa, xb)
         h0 = ops.gn_apply(xa, st0, blk.norm0.weight, blk.norm0.bias, src1=xb, silu=True, resample=rs, eps=blk.norm0.eps)
-        a = ops.conv2d(h0, self.w_fwd(blk.conv0.weight), Cout, 3, bias=blk.conv0.bias)
-        st1 = ops.gn_stats(a)
+        a = self._conv_q(h0, self.w_fwd(blk.conv0.weight), Cout, 3, bias=blk.conv0.bias)
+        st1 = self._stats(a)
         p = float(blk.dropout) if training else 0.0
         h1 = ops.gn_apply(a, st1, blk.norm1.weight, blk.norm1.bias, ada=blk.affine.bias, silu=True, dropout_p=p,
                           seed=seed, eps=blk.norm1.eps)
@@ -147,15 +212,15 @@ class UNetEngine:
             if blk.up or blk.down:
                 raise NotImplementedError('resampling 1x1 skip (resample_proj) is not on the path')
             s = ops.conv2d(xa, self.w_fwd(blk.skip.weight), Cout, 1, bias=blk.skip.bias, src1=xb)
-            y = ops.conv2d(h1, w1, Cout, 3, bias=blk.conv1.bias, residual=s, out=s)
+            y = self._conv_q(h1, w1, Cout, 3, bias=blk.conv1.bias, residual=s, out=s)
         elif blk.up:
             s = ops.upsample2(xa)
-            y = ops.conv2d(h1, w1, Cout, 3, bias=blk.conv1.bias, residual=s, out=s)
+            y = self._conv_q(h1, w1, Cout, 3, bias=blk.conv1.bias, residual=s, out=s)
         elif blk.down:
             s = ops.avgpool2(xa)
-            y = ops.conv2d(h1, w1, Cout, 3, bias=blk.conv1.bias, residual=s, out=s)
+            y = self._conv_q(h1, w1, Cout, 3, bias=blk.conv1.bias, residual=s, out=s)
         else:
-            y = ops.conv2d(h1, w1, Cout, 3, bias=blk.conv1.bias, residual=xa)
+            y = self._conv_q(h1, w1, Cout, 3, bias=blk.conv1.bias, residual=xa)
         rec = None
         if save:
             rec = dict(kind='block', blk=blk, xa=xa, xb=xb, st0=st0, h0=h0, a=a, st1=st1, h1=h1, y=y, p=p, seed=seed,
@@ -164,11 +229,11 @@ class UNetEngine:
         if blk.num_heads:
             heads = blk.num_heads
             perm = self.qkv_perm(Cout, heads, y.device)
-            st2 = ops.gn_stats(y)
+            st2 = self._stats(y)
             h2 = ops.gn_apply(y, st2, blk.norm2.weight, blk.norm2.bias, silu=False, eps=blk.norm2.eps)
             qkv = ops.conv2d(h2, self.w_fwd(blk.qkv.weight, perm), 3 * Cout, 1, bias=self.bias_perm(blk.qkv.bias, perm))
             att, lse = ops.attention_fwd(qkv, heads)
-            out = ops.conv2d(att, self.w_fwd(blk.proj.weight), Cout, 1, bias=blk.proj.bias, residual=y)
+            out = self._conv_q(att, self.w_fwd(blk.proj.weight), Cout, 1, bias=blk.proj.bias, residual=y)
             if save:
                 rec.update(st2=st2, h2=h2, qkv=qkv, att=att, lse=lse, perm=perm)
         if save:
@@ -410,17 +475,17 @@ class GaussianEngine:
         # the bf16 rounding of the encoder WEIGHTS alone moves it by 1e-3..2e-3 (activations: 5e-5); the split keeps the
         # tcgen05 kernel and doubles K of these forward convs (<1 % of the step's FLOPs).
         mode = 2 if self.dtype == torch.bfloat16 else 0
-        return self.cache.get((id(p), 'f', self.dtype, Ci_pad, mode), p,
-                              lambda: ops.pack_weight(p.detach(), mode, self.dtype, Ci_pad=Ci_pad))
+        return self.cache.get_weight((id(p), 'f', self.dtype, Ci_pad, mode), p, self.dtype, mode, Ci_pad=Ci_pad)
 
     def w_dgrad(self, p):
-        return self.cache.get((id(p), 'd', self.dtype), p, lambda: ops.pack_weight(p.detach(), 1, self.dtype))
+        return self.cache.get_weight((id(p), 'd', self.dtype), p, self.dtype, 1)
 
     def convs(self):
         return [m for m in self.net.encoder if isinstance(m, torch.nn.Conv2d)]
 
     def forward(self, xin, save):
         """xin: NHWC [N,H,W,Cin] (x, or x||target for the posterior).  Returns (mu, log_sigma, tape)."""
+        self.cache.refresh()
         convs = self.convs()
         x = xin
         acts = []

@@ -67,6 +67,41 @@ def pack_weight(w, mode, dtype, Ci_pad=None, perm=None, Ci=None, src_co_stride=0
     return out
 
 
+_PACK_DT = None
+
+
+def pack_item(w, out, mode, perm=None, Ci_pad=None, dtype=None):
+    """One row of the pu_pack_conv_weights_multi table (include/probunet_b200.h, PuPackItem) as a tuple."""
+    Co = w.shape[0]
+    k = w.shape[-1] if w.dim() == 4 else 1
+    Ci = w.shape[1]
+    Ci_pad = Ci_pad or Ci
+    tiles = ((Co + 31) // 32) * ((Ci_pad + 31) // 32)
+    return (w.data_ptr(), out.data_ptr(), perm.data_ptr() if perm is not None else 0, Ci * k * k, Co, Ci, k, Ci_pad,
+            mode, dtype_code(dtype if dtype is not None else out.dtype), tiles)
+
+
+def pack_table(items, device):
+    """Device table for pu_pack_conv_weights_multi: returns (table tensor, n_items, total_tiles)."""
+    import numpy as np
+    global _PACK_DT
+    if _PACK_DT is None:
+        _PACK_DT = np.dtype([('src', '<u8'), ('dst', '<u8'), ('perm', '<u8'), ('stride', '<i8'), ('Co', '<i4'),
+                             ('Ci', '<i4'), ('k', '<i4'), ('Ci_pad', '<i4'), ('mode', '<i4'), ('dtype', '<i4'),
+                             ('tile_begin', '<i4'), ('pad', '<i4')])
+    tab = np.zeros(len(items), dtype=_PACK_DT)
+    begin = 0
+    for i, it in enumerate(items):
+        tab[i] = it[:10] + (begin, 0)
+        begin += it[10]
+    host = torch.from_numpy(tab.view(np.uint8).copy())
+    return host.to(device), len(items), begin
+
+
+def pack_weights_multi(table, n_items, total_tiles):
+    check(lib().pu_pack_conv_weights_multi(ptr(table), n_items, total_tiles, stream_ptr()), 'pack_conv_weights_multi')
+
+
 def unpack_wgrad(dw_packed, grad, perm=None, Ci=None, dst_co_stride=0, accumulate=False):
     """dw_packed: fp32 [Co, k, k, Ci_pad]; grad: fp32 OIHW destination."""
     Co, k, _, Ci_pad = dw_packed.shape
@@ -89,16 +124,19 @@ def scatter(src, perm, dst, accumulate=False):
 
 # ----------------------------------------------------------------------------- convolution
 def conv2d(src0, weight, Cout, ksize, bias=None, src1=None, residual=None, relu=False, bias_per_sample=False,
-           out=None, flags=0):
+           out=None, flags=0, want_qstats=False):
+    """want_qstats: also return the [N, Cout/4, 2] fp64 (sum, sumsq) of the stored output per quad of channels, taken in
+    the conv epilogue -- the GroupNorm statistics of whatever consumes the output (gn_stats_from_quads)."""
     N, H, W, C0 = _nhwc(src0)
     C1 = src1.shape[3] if src1 is not None else 0
     if out is None:
         out = torch.empty((N, H, W, Cout), dtype=src0.dtype, device=src0.device)
+    q = torch.empty((N, Cout // 4, 2), dtype=torch.float64, device=src0.device) if want_qstats else None
     a = L.PuConvArgs(N, H, W, C0, C1, Cout, ksize, dtype_code(src0.dtype), flags | (L.CONV_RELU if relu else 0),
                      int(bias_per_sample), ptr(src0), ptr(src1), ptr(weight), ptr(bias), ptr(residual), ptr(out),
-                     None, 0)
+                     ptr(q), 0)
     check(lib().pu_conv2d(C.byref(a), stream_ptr()), 'conv2d')
-    return out
+    return (out, q) if want_qstats else out
 
 
 def conv2d_wgrad(src0, dy, ksize, src1=None, dw=None, accumulate=False, flags=0):
@@ -137,6 +175,17 @@ def gn_stats(src0, src1=None, G=None):
     stats = torch.empty((N, G, 2), dtype=torch.float64, device=src0.device)
     check(lib().pu_gn_stats(ptr(src0), ptr(src1), C0, C1, N, H * W, G, dtype_code(src0.dtype), ptr(stats),
                             stream_ptr()), 'gn_stats')
+    return stats
+
+
+def gn_stats_from_quads(q0, q1=None, G=None):
+    """GroupNorm statistics [N, G, 2] of a tensor (or the channel concatenation of two) from the per-quad statistics that
+    the producing convolutions emitted (conv2d(..., want_qstats=True))."""
+    N, C0 = q0.shape[0], q0.shape[1] * 4
+    C1 = q1.shape[1] * 4 if q1 is not None else 0
+    G = G or gn_groups(C0 + C1)
+    stats = torch.empty((N, G, 2), dtype=torch.float64, device=q0.device)
+    check(lib().pu_gn_stats_from_quads(ptr(q0), ptr(q1), C0, C1, N, G, ptr(stats), stream_ptr()), 'gn_stats_from_quads')
     return stats
 
 

@@ -155,6 +155,70 @@ def test_conv_tc_fwd(case):
     assert e0 < 6e-3 and e1 < 6e-3
 
 
+def test_pack_weights_multi_matches_single_packs():
+    """pu_pack_conv_weights_multi (one launch for many weights) == pu_pack_conv_weight item by item: forward, data-gradient
+    and hi/lo split layouts, 3x3 and 1x1, a row permutation, zero-padded input channels, sizes that are not multiples of
+    the 32x32 tile, bf16 and fp32 destinations."""
+    cases = [  # Co, Ci, k, mode, Ci_pad, perm?, dtype
+        (64, 3, 3, 0, 64, False, torch.bfloat16), (128, 64, 3, 0, None, False, torch.bfloat16),
+        (128, 64, 3, 1, None, False, torch.bfloat16), (192, 64, 1, 0, None, True, torch.bfloat16),
+        (192, 64, 1, 1, None, True, torch.bfloat16), (64, 6, 3, 2, 64, False, torch.bfloat16),
+        (40, 50, 3, 0, None, False, torch.float32), (40, 50, 3, 1, None, False, torch.float32),
+        (20, 7, 1, 0, 16, False, torch.float32), (256, 128, 3, 2, None, False, torch.bfloat16),
+    ]
+    items, outs, refs = [], [], []
+    for i, (Co, Ci, k, mode, Ci_pad, use_perm, dt) in enumerate(cases):
+        w = rnd(Co, Ci, k, k, seed=40 + i)
+        perm = torch.randperm(Co, generator=torch.Generator().manual_seed(i)).to(torch.int32).to(DEV) if use_perm else None
+        ref = ops.pack_weight(w, mode, dt, perm=perm, Ci_pad=Ci_pad)
+        out = torch.full_like(ref, float('nan'))
+        items.append(ops.pack_item(w, out, mode, perm=perm, Ci_pad=Ci_pad, dtype=dt))
+        outs.append(out)
+        refs.append((ref, w, perm))
+    table, n, tiles = ops.pack_table(items, torch.device(DEV))
+    ops.pack_weights_multi(table, n, tiles)
+    for case, out, (ref, _, _) in zip(cases, outs, refs):
+        assert torch.equal(out, ref), case
+
+
+@pytest.mark.parametrize('case', CONV_CASES)
+@pytest.mark.parametrize('impl', ['simple_f32', 'tc'])
+def test_conv_epilogue_quad_stats(case, impl):
+    """GroupNorm statistics from the producing conv's epilogue (PuConvArgs.qstats): per sample and quad of channels the sum
+    and the sum of squares of the output AS STORED; pu_gn_stats_from_quads folds them into [N, G, 2], also for the channel
+    concatenation of two producers, and must agree with the stand-alone statistics pass (pu_gn_stats)."""
+    N, H, W, C0, C1, Co, k = case
+    dt = torch.float32 if impl == 'simple_f32' else torch.bfloat16
+    flags = L.CONV_FORCE_SIMPLE if impl == 'simple_f32' else L.CONV_FORCE_TC
+    x = rnd(N, C0 + C1, H, W, seed=1).to(dt).float()
+    w = (rnd(Co, C0 + C1, k, k, seed=2) / math.sqrt((C0 + C1) * k * k)).to(dt).float()
+    b = rnd(Co, seed=3)
+    res = rnd(N, Co, H, W, seed=4).to(dt).float()
+    xs = nhwc(x, dt)
+    s0 = xs[..., :C0].contiguous()
+    s1 = xs[..., C0:].contiguous() if C1 else None
+    y, q = ops.conv2d(s0, ops.pack_weight(w, 0, dt), Co, k, bias=b, src1=s1, residual=nhwc(res, dt), flags=flags,
+                      want_qstats=True)
+    yf = y.double().reshape(N, H * W, Co // 4, 4)
+    want = torch.stack([yf.sum(dim=(1, 3)), (yf * yf).sum(dim=(1, 3))], dim=-1)
+    err = ((q - want).abs() / (want.abs() + 1e-3 * H * W)).max().item()
+    print(f'qstats {impl} {case}: max rel err {err:.3e}')
+    assert q.shape == (N, Co // 4, 2) and err < 2e-5
+    G = ops.gn_groups(Co) if Co >= 128 else Co // 4
+    st = ops.gn_stats_from_quads(q, G=G)
+    st_ref = ops.gn_stats(y, G=G)
+    assert ((st - st_ref).abs() / (st_ref.abs() + 1e-3 * H * W)).max().item() < 2e-5
+    # concatenation of two producers whose boundary is not a multiple of the group size: 64 || Co channels
+    other = nhwc(rnd(N, 64, H, W, seed=9), dt)
+    qo = torch.stack([other.double().reshape(N, H * W, 16, 4).sum(dim=(1, 3)),
+                      (other.double() ** 2).reshape(N, H * W, 16, 4).sum(dim=(1, 3))], dim=-1).contiguous()
+    Ct = 64 + Co
+    Gc = next(g for g in (32, 16, 8, 4, 2, 1) if Ct % g == 0 and (Ct // g) % 4 == 0)
+    st2 = ops.gn_stats_from_quads(qo, q, G=Gc)
+    st2_ref = ops.gn_stats(other, y, G=Gc)
+    assert ((st2 - st2_ref).abs() / (st2_ref.abs() + 1e-3 * H * W)).max().item() < 2e-5
+
+
 @pytest.mark.parametrize('case', CONV_CASES)
 @pytest.mark.parametrize('impl', ['simple_f32', 'tc'])
 def test_conv_dgrad(case, impl):
