@@ -84,6 +84,22 @@ int pu_gather_f32(const float* src, const int* perm, float* dst, int n, void* st
 int pu_scatter_f32(const float* src, const int* perm, float* dst, int n, int accumulate, void* stream);
 
 /* ---------------- convolution (networks.py:87 F.conv2d; prob_unet.py:33,41-42,93-97 nn.Conv2d) ---------------- */
+/* Optional epilogue of a DATA-GRADIENT conv whose output is the gradient wrt the output y of
+ *     y = dropout(act(u)),  u = xhat * gamma' + beta',  xhat = GroupNorm(x)        (networks.py:164-175)
+ * i.e. of the conv that consumes a GroupNorm(+SiLU)(+dropout) result.  The epilogue turns the accumulator g = dL/dy
+ * into du = dL/du (dropout mask, SiLU derivative) while it is still in registers, stores du instead of g, and
+ * accumulates the two per-(sample, channel) sums of the GroupNorm backward -- the first pass of pu_gn_bwd, which is
+ * then called with du_ready = 1 and only runs its second pass.  Requires the tcgen05 kernel (bf16, 64-multiples). */
+typedef struct PuConvGnBwd {
+    const void* x0;       /* the normalised tensor x (pre-norm activation), NHWC, C0 channels ...          */
+    const void* x1;       /* ... and the second source of a concatenation (C1 channels) or NULL           */
+    int C0, C1;           /* C0 + C1 == Cout of the conv                                                  */
+    const float* consts;  /* [N][C][4] = (rstd*gamma', beta' - mean*rstd*gamma', rstd, -mean*rstd): pu_gn_bwd_consts */
+    double* sums;         /* [N][C][2]: receives sum_pixels du and sum_pixels du*xhat; zeroed by the call  */
+    int silu;
+    float dropout_p;
+    unsigned long long seed;
+} PuConvGnBwd;
 typedef struct PuConvArgs {
     int N, H, W;          /* output == input spatial size (stride 1, padding k/2)                     */
     int C0, C1;           /* input channels of src0 / src1 (C1 = 0: single source).  src0||src1 is the */
@@ -106,6 +122,7 @@ typedef struct PuConvArgs {
                           /* that is a multiple of 4, also over a channel concatenation of two such tensors, are  */
                           /* formed from the quads by pu_gn_stats_from_quads                                      */
     int reserved;         /* must be 0                                                                            */
+    const PuConvGnBwd* gn_bwd; /* optional GroupNorm-backward epilogue (see above) or NULL                          */
 } PuConvArgs;
 /* forward conv and, with a mode-1 packed weight, data gradient (convolution_backward's grad_input) */
 int pu_conv2d(const PuConvArgs* a, void* stream);
@@ -166,8 +183,13 @@ typedef struct PuGnBwdArgs {
     int acc_params;
     float* colsum0;       /* optional [C0]: sum over (n, pixels) of the final dx0 values written (incl. dres  */
     float* colsum1;       /* and the accumulated old value) = bias gradient of the conv that produced src0/1  */
+    int du_ready;         /* 1: dy already holds du and sums is filled (PuConvArgs.gn_bwd epilogue of the conv that */
+                          /* produced dy): only the second pass runs.  Needs resample == dres_resample == NONE ... */
 } PuGnBwdArgs;
 int pu_gn_bwd(const PuGnBwdArgs* a, void* stream);
+/* consts[n][c] = the four per-(sample, channel) constants of PuConvGnBwd, from the forward call's statistics and affine
+ * parameters (f->y unused) */
+int pu_gn_bwd_consts(const PuGnArgs* f, float* consts, void* stream);
 
 /* ---------------- attention (networks.py:112-125,179-184) ---------------- */
 /* qkv is NHWC-flattened [N][T][3*C] with channel order (j in {q,k,v}, head, d) -- the product's own order,

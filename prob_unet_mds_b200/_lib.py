@@ -17,11 +17,17 @@ CONV_RELU, CONV_FORCE_SIMPLE, CONV_FORCE_TC = 1, 2, 4
 c_void_p, c_int, c_float, c_ll, c_ull = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_ulonglong
 
 
+class PuConvGnBwd(C.Structure):
+    _fields_ = [('x0', c_void_p), ('x1', c_void_p), ('C0', c_int), ('C1', c_int), ('consts', c_void_p),
+                ('sums', c_void_p), ('silu', c_int), ('dropout_p', c_float), ('seed', c_ull)]
+
+
 class PuConvArgs(C.Structure):
     _fields_ = [('N', c_int), ('H', c_int), ('W', c_int), ('C0', c_int), ('C1', c_int), ('Cout', c_int),
                 ('ksize', c_int), ('dtype', c_int), ('flags', c_int), ('bias_per_sample', c_int),
                 ('src0', c_void_p), ('src1', c_void_p), ('weight', c_void_p), ('bias', c_void_p),
-                ('residual', c_void_p), ('out', c_void_p), ('qstats', c_void_p), ('reserved', c_int)]
+                ('residual', c_void_p), ('out', c_void_p), ('qstats', c_void_p), ('reserved', c_int),
+                ('gn_bwd', C.POINTER(PuConvGnBwd))]
 
 
 class PuWgradArgs(C.Structure):
@@ -41,7 +47,7 @@ class PuGnBwdArgs(C.Structure):
     _fields_ = [('f', PuGnArgs), ('dy', c_void_p), ('dres', c_void_p), ('dres_resample', c_int),
                 ('sums', c_void_p), ('dx0', c_void_p), ('dx1', c_void_p), ('acc0', c_int), ('acc1', c_int),
                 ('dgamma', c_void_p), ('dbeta', c_void_p), ('dada', c_void_p), ('acc_params', c_int),
-                ('colsum0', c_void_p), ('colsum1', c_void_p)]
+                ('colsum0', c_void_p), ('colsum1', c_void_p), ('du_ready', c_int)]
 
 
 class PuFcombArgs(C.Structure):
@@ -72,6 +78,7 @@ _SIGNATURES = {
     'pu_gn_stats_from_quads': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'pu_gn_apply': (c_int, [C.POINTER(PuGnArgs), c_void_p]),
     'pu_gn_bwd': (c_int, [C.POINTER(PuGnBwdArgs), c_void_p]),
+    'pu_gn_bwd_consts': (c_int, [C.POINTER(PuGnArgs), c_void_p, c_void_p]),
     'pu_attention_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'pu_attention_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                  c_int, c_int, c_int, c_void_p]),

@@ -159,6 +159,15 @@ struct ConvTcParams {
     const __nv_bfloat16* residual;
     __nv_bfloat16* out;
     double* qstats;         // [N][Cout/4][2] or nullptr
+    // GroupNorm-backward epilogue (PuConvGnBwd), x0 == nullptr: off
+    const __nv_bfloat16* gx0;
+    const __nv_bfloat16* gx1;
+    int gC0, gC1;
+    const float4* gconsts;
+    double* gsums;
+    int gsilu;
+    float gdrop;
+    unsigned long long gseed;
 };
 
 // Sums each of 16 per-lane values over the 32 lanes of the warp with 16 shuffles (recursive halving: at every step a
@@ -176,6 +185,36 @@ __device__ __forceinline__ float warp_reduce_scatter16(float (&v)[16], int lane)
         }
     }
     return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+// The same for 32 values val(0..31) (31 shuffles): returns the warp total of val(lane).  The values are produced on
+// demand by `val`, so only 16 of them are live at a time.
+template <typename F>
+__device__ __forceinline__ float warp_reduce_scatter32(F&& val, int lane) {
+    float v[16];
+    {
+        const bool up = (lane & 16) != 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float a = val(i), b = val(i + 16);
+            v[i] = (up ? b : a) + __shfl_xor_sync(0xffffffffu, up ? a : b, 16);
+        }
+    }
+#pragma unroll
+    for (int h = 8; h >= 1; h >>= 1) {
+        const bool up = (lane & h) != 0;
+#pragma unroll
+        for (int i = 0; i < h; ++i) {
+            const float send = up ? v[i] : v[i + h];
+            const float keep = up ? v[i + h] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+        }
+    }
+    return v[0];
+}
+__device__ __forceinline__ float sigmoid_fast(float u) {       // 0.5 tanh(u/2) + 0.5, one MUFU (as gn.cu's bf16 kernels)
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * u));
+    return fmaf(t, 0.5f, 0.5f);
 }
 
 constexpr int TILE_W = 16, TILE_H = 8;      // 128 output pixels per CTA tile
@@ -197,7 +236,8 @@ struct ConvTcCfg {
     static constexpr int SMEM = STAGES * (A_STAGE + B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN, int MT>
+// GNB = true: the epilogue is the GroupNorm-backward one (PuConvGnBwd) and nothing else (no bias / residual / ReLU)
+template <int BN, int MT, bool GNB = false>
 __global__ void __launch_bounds__(384, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const ConvTcParams p) {
@@ -352,6 +392,73 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 float f[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                if constexpr (GNB) {
+                    // ---- GroupNorm-backward epilogue: g = dL/dy (accumulator) -> du = dL/du, stored instead of g;
+                    // per-(sample, channel) sums of du and du * xhat over the tile's pixels -> p.gsums (fp64 atomics)
+                    const int Cn = p.gC0 + p.gC1;
+                    const int ch0 = n0 + c;                              // first channel of this chunk in x
+                    uint32_t xr[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) xr[j] = 0u;
+                    uint32_t keep = 0xffffffffu;
+                    if (valid) {
+                        const __nv_bfloat16* xp = ch0 < p.gC0 ? p.gx0 + pix * p.gC0 + ch0 : p.gx1 + pix * p.gC1 + (ch0 - p.gC0);
+                        asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                     : "=r"(xr[0]), "=r"(xr[1]), "=r"(xr[2]), "=r"(xr[3]), "=r"(xr[4]), "=r"(xr[5]),
+                                       "=r"(xr[6]), "=r"(xr[7])
+                                     : "l"(xp));
+                        asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                     : "=r"(xr[8]), "=r"(xr[9]), "=r"(xr[10]), "=r"(xr[11]), "=r"(xr[12]), "=r"(xr[13]),
+                                       "=r"(xr[14]), "=r"(xr[15])
+                                     : "l"(xp + 16));
+                        if (p.gdrop > 0.f) {
+                            keep = 0u;
+                            const unsigned long long e8 = (unsigned long long)((pix * Cn + ch0) >> 3);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) keep |= dropout_keep8(p.gseed, e8 + i, p.gdrop) << (8 * i);
+                        }
+                    } else {
+                        keep = 0u;
+                    }
+                    const float inv_keep = p.gdrop > 0.f ? 1.f / (1.f - p.gdrop) : 1.f;
+                    const float4* kc = p.gconsts + (long long)img * Cn + ch0;
+                    auto xval = [&](int j) {
+                        const __nv_bfloat162 xx = *reinterpret_cast<const __nv_bfloat162*>(&xr[j >> 1]);
+                        return (j & 1) ? __high2float(xx) : __low2float(xx);
+                    };
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float gg = ((keep >> j) & 1u) ? f[j] : 0.f;
+                        if (p.gsilu) {
+                            const float2 k2 = __ldg(reinterpret_cast<const float2*>(kc + j));   // (ag, bg) of channel ch0 + j
+                            const float u = fmaf(xval(j), k2.x, k2.y);
+                            const float s = sigmoid_fast(u);
+                            gg *= (s * inv_keep) * fmaf(u, 1.f - s, 1.f);
+                        } else {
+                            gg *= inv_keep;
+                        }
+                        f[j] = gg;
+                    }
+                    if (valid) {
+                        __nv_bfloat16* op = p.out + pix * p.Cout + n0 + c;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 16) {
+                            float ov[16];
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) ov[e] = f[j + e];
+                            st16(op + j, ov);
+                        }
+                    }
+                    // sum over the tile's pixels (lanes) of du * xhat and of du; lane l ends up with channel ch0 + l
+                    const float sb = warp_reduce_scatter32([&](int j) {
+                        const float2 k2 = __ldg(reinterpret_cast<const float2*>(kc + j) + 1);      // (rstd, -mean * rstd)
+                        return f[j] * fmaf(xval(j), k2.x, k2.y);
+                    }, lane);
+                    const float sa = warp_reduce_scatter32([&](int j) { return f[j]; }, lane);
+                    double* sp = p.gsums + ((long long)img * Cn + ch0 + lane) * 2;
+                    atomicAdd(sp, (double)sa);
+                    atomicAdd(sp + 1, (double)sb);
+                } else {
                 if (bias) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] += __ldg(bias + c + j);
@@ -403,6 +510,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         atomicAdd(p.qstats + ((long long)img * (p.Cout >> 2) + ((n0 + c) >> 2)) * 2 + idx, (double)tot);
                     }
                 }
+                }   // !GNB
             }
             tc_fence_before();
             __syncwarp();
@@ -904,8 +1012,11 @@ bool conv_tc_applicable(const PuConvArgs* a) {
     return true;
 }
 
-template <int BN, int MT>
+template <int BN, int MT, bool GNB = false>
 static int conv_tc_launch_bn(const PuConvArgs* a, cudaStream_t st) {
+    if constexpr (!GNB) {
+        if (a->gn_bwd) return conv_tc_launch_bn<BN, MT, true>(a, st);
+    }
     using Cfg = ConvTcCfg<BN, MT>;
     ConvTcParams p;
     p.N = a->N; p.H = a->H; p.W = a->W; p.Cout = a->Cout; p.ksize = a->ksize;
@@ -924,6 +1035,19 @@ static int conv_tc_launch_bn(const PuConvArgs* a, cudaStream_t st) {
     p.residual = (const __nv_bfloat16*)a->residual;
     p.out = (__nv_bfloat16*)a->out;
     p.qstats = a->qstats;
+    p.gx0 = nullptr;
+    if (a->gn_bwd) {
+        const PuConvGnBwd* g = a->gn_bwd;
+        p.gx0 = (const __nv_bfloat16*)g->x0;
+        p.gx1 = (const __nv_bfloat16*)g->x1;
+        p.gC0 = g->C0;
+        p.gC1 = g->C1;
+        p.gconsts = (const float4*)g->consts;
+        p.gsums = g->sums;
+        p.gsilu = g->silu;
+        p.gdrop = g->dropout_p;
+        p.gseed = g->seed;
+    }
 
     CUtensorMap tA0, tA1, tB;
     int rc = make_act_tmap(&tA0, a->src0, a->N, a->H, a->W, a->C0, TILE_W, TILE_H);
@@ -936,9 +1060,9 @@ static int conv_tc_launch_bn(const PuConvArgs* a, cudaStream_t st) {
     rc = make_mat_tmap(&tB, a->weight, a->Cout, (long long)a->ksize * a->ksize * (a->C0 + a->C1), BN);
     if (rc) return rc;
 
-    PU_SMEM_ATTR((conv_tc_kernel<BN, MT>), Cfg::SMEM);
+    PU_SMEM_ATTR((conv_tc_kernel<BN, MT, GNB>), Cfg::SMEM);
     int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-    conv_tc_kernel<BN, MT><<<grid, 384, Cfg::SMEM, st>>>(tA0, tA1, tB, p);
+    conv_tc_kernel<BN, MT, GNB><<<grid, 384, Cfg::SMEM, st>>>(tA0, tA1, tB, p);
     return check_launch("conv_tc");
 }
 
@@ -1079,6 +1203,18 @@ extern "C" int pu_conv2d(const PuConvArgs* a, void* stream) {
         PU_REQUIRE(tc, "pu_conv2d: PU_CONV_FORCE_TC but the tcgen05 kernel does not apply (dtype=%d C0=%d C1=%d Cout=%d)",
                    a->dtype, a->C0, a->C1, a->Cout);
     if (a->qstats) PU_CUDA(cudaMemsetAsync(a->qstats, 0, sizeof(double) * 2 * (size_t)a->N * (a->Cout / 4), st));
+    if (a->gn_bwd) {
+        const PuConvGnBwd* g = a->gn_bwd;
+        PU_REQUIRE(tc, "pu_conv2d: the GroupNorm-backward epilogue needs the tcgen05 kernel (bf16, channels %% 64 == 0, "
+                       "image >= 8x16); got dtype=%d C0=%d C1=%d Cout=%d %dx%d", a->dtype, a->C0, a->C1, a->Cout, a->H, a->W);
+        PU_REQUIRE(g->x0 && g->consts && g->sums && g->C0 > 0 && g->C1 >= 0 && g->C0 + g->C1 == a->Cout &&
+                   g->C0 % 32 == 0 && g->C1 % 32 == 0 && (g->C1 == 0 || g->x1),
+                   "pu_conv2d: bad gn_bwd epilogue (C0=%d C1=%d Cout=%d)", g->C0, g->C1, a->Cout);
+        PU_REQUIRE(!a->bias && !a->residual && !(a->flags & PU_CONV_RELU) && !a->qstats,
+                   "pu_conv2d: the gn_bwd epilogue excludes bias / residual / ReLU / qstats");
+        PU_REQUIRE(g->dropout_p >= 0.f && g->dropout_p < 1.f, "pu_conv2d: bad gn_bwd dropout p");
+        PU_CUDA(cudaMemsetAsync(g->sums, 0, sizeof(double) * 2 * (size_t)a->N * a->Cout, st));
+    }
     if (tc) return pu::conv_tc_launch(a, st);
     pu::note_fallback("pu_conv2d", a->dtype, a->C0, a->C1, a->Cout, a->H, a->W);
     int rc = pu::conv_simple_launch(a, st);

@@ -735,6 +735,28 @@ __global__ void gn_bwd_params_kernel(PuGnBwdArgs a) {
     }
 }
 
+// the per-(sample, channel) constants of the conv epilogue that takes over the reduce pass (PuConvGnBwd.consts)
+__global__ void gn_bwd_consts_kernel(PuGnArgs f, float4* __restrict__ out) {
+    const int C = f.C0 + f.C1;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= f.N * C) return;
+    const int n = i / C, c = i - n * C;
+    const int Cg = C / f.G, g = c / Cg;
+    const double m = (double)Cg * f.H * f.W;
+    const double mm = f.stats[((long long)n * f.G + g) * 2] / m;
+    double var = f.stats[((long long)n * f.G + g) * 2 + 1] / m - mm * mm;
+    if (var < 0) var = 0;
+    const float mean = (float)mm;
+    const float rstd = (float)(1.0 / sqrt(var + (double)f.eps));
+    float gam = f.gamma[c], bet = f.beta[c];
+    if (f.ada) {
+        const float sc = f.ada[c], sh = f.ada[C + c];
+        gam = gam * (1.f + sc);
+        bet = fmaf(bet, 1.f + sc, sh);
+    }
+    out[i] = make_float4(rstd * gam, fmaf(-mean * rstd, gam, bet), rstd, -mean * rstd);
+}
+
 // pixel rows per block: aim at ~8 blocks per SM over the whole launch, but at least `min_rows` rows of work
 // The grid is (chunks per sample, N) with 3 resident blocks per SM (launch bounds): choose the chunk count (up to ~3
 // waves) whose last wave is fullest -- e.g. N = 64: 13 chunks -> 832 blocks = 1.87 waves of 444 instead of
@@ -832,6 +854,16 @@ int pu_gn_apply(const PuGnArgs* a, void* stream) {
     return check_launch("gn_apply");
 }
 
+int pu_gn_bwd_consts(const PuGnArgs* f, float* consts, void* stream) {
+    using namespace pu;
+    PU_REQUIRE(f && consts, "pu_gn_bwd_consts: null pointer");
+    int rc = check_gn(*f, "pu_gn_bwd_consts");
+    if (rc) return rc;
+    const int total = f->N * (f->C0 + f->C1);
+    gn_bwd_consts_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(*f, reinterpret_cast<float4*>(consts));
+    return check_launch("gn_bwd_consts");
+}
+
 int pu_gn_bwd(const PuGnBwdArgs* a, void* stream) {
     using namespace pu;
     PU_REQUIRE(a && a->dy && a->sums && a->dx0 && a->dgamma && a->dbeta, "pu_gn_bwd: null pointer");
@@ -839,14 +871,16 @@ int pu_gn_bwd(const PuGnBwdArgs* a, void* stream) {
     if (rc) return rc;
     const PuGnArgs& f = a->f;
     PU_REQUIRE(f.C1 == 0 || a->dx1, "pu_gn_bwd: C1 > 0 needs dx1");
+    PU_REQUIRE(!a->du_ready || (f.resample == PU_RS_NONE && (!a->dres || a->dres_resample == PU_RS_NONE)),
+               "pu_gn_bwd: du_ready needs resample == dres_resample == PU_RS_NONE");
     cudaStream_t st = (cudaStream_t)stream;
     const int C = f.C0 + f.C1;
     const int HW = f.H * f.W;
-    PU_CUDA(cudaMemsetAsync(a->sums, 0, sizeof(double) * 2 * f.N * C, st));
     const int PL = GN_THREADS / (C / 8);
     const int rows = rows_per_block(HW, f.N, PL * 8, GN_BWD_BLOCKS);
     dim3 grid(cdiv(HW, rows), f.N);
-    {
+    if (!a->du_ready) {
+        PU_CUDA(cudaMemsetAsync(a->sums, 0, sizeof(double) * 2 * f.N * C, st));
         const size_t smem = sizeof(float) * 2 * C;
         if (f.dtype == PU_F32)
             gn_bwd_reduce_kernel<float, false><<<grid, GN_THREADS, smem, st>>>(*a, rows);

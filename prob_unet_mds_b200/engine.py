@@ -148,7 +148,10 @@ class UNetEngine:
         # GroupNorm statistics come out of the producing convolutions' epilogues (per quad of channels); self._q maps an
         # activation tensor to them for its consumers (the next block's norm0, also across a skip concatenation)
         self._q = {}
-        self._fused_stats = os.environ.get('PROBUNET_B200_FUSED_GN_STATS', '1') != '0'
+        # (quads need group sizes that are multiples of 4: model_channels % 128 == 0 -- true for the Probabilistic U-Net's
+        # backbone, not for the 64-channel deterministic baseline, whose 192-channel levels have groups of 6)
+        self._fused_stats = (os.environ.get('PROBUNET_B200_FUSED_GN_STATS', '1') != '0'
+                             and u.model_channels % 128 == 0)
         self.cache.refresh()
         for name, mod in u.enc.items():
             if isinstance(mod, torch.nn.Module) and hasattr(mod, 'norm0'):
@@ -278,9 +281,20 @@ class UNetEngine:
             torch.cuda.current_stream().wait_stream(self._side)
             self._side_used = False
 
+    def _dgrad_gn(self, dy, w, Cin, k, x0, st, norm, x1=None, ada=None, silu=True, p=0.0, seed=0, rs=L.RS_NONE):
+        """Data gradient of a conv whose input was GroupNorm(+SiLU)(+dropout) of x0 (|| x1).  Where the tcgen05 kernel
+        applies (and no resampling sits between the norm and the conv) its epilogue already does the first pass of the
+        GroupNorm backward: it returns du = dL/du and the per-(sample, channel) sums; otherwise (dL/dh, None)."""
+        if self._fused_gn_bwd and rs == L.RS_NONE and ops.conv_tc_applies(dy, 0, Cin):
+            d, sums, _ = ops.gn_bwd_epilogue(x0, st, norm.weight, norm.bias, src1=x1, ada=ada, silu=silu, dropout_p=p,
+                                             seed=seed, eps=norm.eps)
+            return ops.conv2d(dy, w, Cin, k, gn_bwd=d), sums
+        return ops.conv2d(dy, w, Cin, k), None
+
     def backward(self, tape, dfeat, grads):
         """dfeat: NHWC gradient wrt the features.  Fills grads[id(param)] for every live parameter."""
         u = self.unet
+        self._fused_gn_bwd = os.environ.get('PROBUNET_B200_FUSED_GN_BWD', '1') != '0'
         gbuf = {}   # id(activation tensor) -> gradient tensor accumulated so far
         self._gsum = {}   # id(gradient tensor) -> its per-channel sums (= bias gradient of the producing conv),
                           # emitted by the gn_bwd call that wrote the tensor last
@@ -289,13 +303,14 @@ class UNetEngine:
         # order everywhere below: data gradient first, then the weight gradient (side stream, starts once the dgrad
         # has finished) so that it runs under the GroupNorm-backward kernels that follow on the main stream
         grads[id(u.out_conv.bias)] = ops.bias_grad(dfeat)
-        dh = ops.conv2d(dfeat, self.w_dgrad(u.out_conv.weight), rec['h'].shape[3], 3)
+        dh, sums = self._dgrad_gn(dfeat, self.w_dgrad(u.out_conv.weight), rec['h'].shape[3], 3, rec['x'], rec['st'],
+                                  u.out_norm)
         self._wgrad(grads, u.out_conv.weight, rec['h'], dfeat, 3)
         dg = torch.empty_like(u.out_norm.weight)
         db = torch.empty_like(u.out_norm.bias)
         cs = torch.empty(rec['x'].shape[3], dtype=torch.float32, device=dh.device)
         dx, _ = ops.gn_bwd(rec['x'], rec['st'], u.out_norm.weight, u.out_norm.bias, dh, dg, db, silu=True,
-                           eps=u.out_norm.eps, colsum0=cs)
+                           eps=u.out_norm.eps, colsum0=cs, sums=sums, du_ready=sums is not None)
         grads[id(u.out_norm.weight)] = dg
         grads[id(u.out_norm.bias)] = db
         gbuf[id(rec['x'])] = dx
@@ -328,13 +343,14 @@ class UNetEngine:
             gq = torch.empty_like(blk.qkv.bias)
             ops.scatter(dbq, perm, gq)
             grads[id(blk.qkv.bias)] = gq
-            dh2 = ops.conv2d(dqkv, self.w_dgrad(blk.qkv.weight, perm), Cout, 1)
+            dh2, sums = self._dgrad_gn(dqkv, self.w_dgrad(blk.qkv.weight, perm), Cout, 1, rec['y'], rec['st2'], blk.norm2,
+                                       silu=False)
             self._wgrad(grads, blk.qkv.weight, rec['h2'], dqkv, 1, perm=perm)
             dg = torch.empty_like(blk.norm2.weight)
             db = torch.empty_like(blk.norm2.bias)
             cs = torch.empty(Cout, dtype=torch.float32, device=dz.device)
             dy, _ = ops.gn_bwd(rec['y'], rec['st2'], blk.norm2.weight, blk.norm2.bias, dh2, dg, db, silu=False,
-                               eps=blk.norm2.eps, dres=dz, colsum0=cs)
+                               eps=blk.norm2.eps, dres=dz, colsum0=cs, sums=sums, du_ready=sums is not None)
             self._gsum[id(dy)] = cs
             grads[id(blk.norm2.weight)] = dg
             grads[id(blk.norm2.bias)] = db
@@ -343,22 +359,24 @@ class UNetEngine:
         # conv1
         bias_dy = self._colsum(dy)
         grads[id(blk.conv1.bias)] = bias_dy
-        dh1 = ops.conv2d(dy, self.w_dgrad(blk.conv1.weight), Cout, 3)
+        dh1, sums = self._dgrad_gn(dy, self.w_dgrad(blk.conv1.weight), Cout, 3, rec['a'], rec['st1'], blk.norm1,
+                                   ada=blk.affine.bias, p=rec['p'], seed=rec['seed'])
         self._wgrad(grads, blk.conv1.weight, rec['h1'], dy, 3)
         dg = torch.empty_like(blk.norm1.weight)
         db = torch.empty_like(blk.norm1.bias)
         dada = torch.empty_like(blk.affine.bias)
         cs = torch.empty(Cout, dtype=torch.float32, device=dy.device)
         da, _ = ops.gn_bwd(rec['a'], rec['st1'], blk.norm1.weight, blk.norm1.bias, dh1, dg, db, ada=blk.affine.bias,
-                           dada=dada, silu=True, dropout_p=rec['p'], seed=rec['seed'], eps=blk.norm1.eps, colsum0=cs)
+                           dada=dada, silu=True, dropout_p=rec['p'], seed=rec['seed'], eps=blk.norm1.eps, colsum0=cs,
+                           sums=sums, du_ready=sums is not None)
         grads[id(blk.norm1.weight)] = dg
         grads[id(blk.norm1.bias)] = db
         grads[id(blk.affine.bias)] = dada
         # conv0
         grads[id(blk.conv0.bias)] = cs
-        dh0 = ops.conv2d(da, self.w_dgrad(blk.conv0.weight), Cin, 3)
-        # skip branch
         rs = rec['rs']
+        dh0, sums0 = self._dgrad_gn(da, self.w_dgrad(blk.conv0.weight), Cin, 3, xa, rec['st0'], blk.norm0, x1=xb, rs=rs)
+        # skip branch
         if blk.skip is not None and blk.skip.weight is not None:
             grads[id(blk.skip.bias)] = ops.clone(bias_dy)   # same values as conv1.bias' gradient, own storage
             dres = ops.conv2d(dy, self.w_dgrad(blk.skip.weight), Cin, 1)
@@ -376,7 +394,8 @@ class UNetEngine:
         csb = torch.empty(xb.shape[3], dtype=torch.float32, device=dy.device) if xb is not None else None
         dxa, dxb = ops.gn_bwd(xa, rec['st0'], blk.norm0.weight, blk.norm0.bias, dh0, dg, db, src1=xb, silu=True,
                               resample=rs, eps=blk.norm0.eps, dres=dres, dres_resample=dres_rs,
-                              dx0=ga, dx1=gb, acc0=ga is not None, acc1=gb is not None, colsum0=csa, colsum1=csb)
+                              dx0=ga, dx1=gb, acc0=ga is not None, acc1=gb is not None, colsum0=csa, colsum1=csb,
+                              sums=sums0, du_ready=sums0 is not None)
         grads[id(blk.norm0.weight)] = dg
         grads[id(blk.norm0.bias)] = db
         gbuf[id(xa)] = dxa

@@ -129,6 +129,7 @@ class UNet(torch.nn.Module):
             raise NotImplementedError('the Probabilistic U-Net path uses label_dim=0, augment_dim=0, use_diffuse=False')
         assert len(img_resolution) == 2
         self.label_dropout = label_dropout
+        self.model_channels = model_channels
         emb_channels = model_channels * channel_mult_emb
         init = dict(init_mode='kaiming_uniform', init_weight=np.sqrt(1 / 3), init_bias=np.sqrt(1 / 3))
         init_zero = dict(init_mode='kaiming_uniform', init_weight=0, init_bias=0)

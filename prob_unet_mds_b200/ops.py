@@ -124,7 +124,7 @@ def scatter(src, perm, dst, accumulate=False):
 
 # ----------------------------------------------------------------------------- convolution
 def conv2d(src0, weight, Cout, ksize, bias=None, src1=None, residual=None, relu=False, bias_per_sample=False,
-           out=None, flags=0, want_qstats=False):
+           out=None, flags=0, want_qstats=False, gn_bwd=None):
     """want_qstats: also return the [N, Cout/4, 2] fp64 (sum, sumsq) of the stored output per quad of channels, taken in
     the conv epilogue -- the GroupNorm statistics of whatever consumes the output (gn_stats_from_quads)."""
     N, H, W, C0 = _nhwc(src0)
@@ -134,9 +134,30 @@ def conv2d(src0, weight, Cout, ksize, bias=None, src1=None, residual=None, relu=
     q = torch.empty((N, Cout // 4, 2), dtype=torch.float64, device=src0.device) if want_qstats else None
     a = L.PuConvArgs(N, H, W, C0, C1, Cout, ksize, dtype_code(src0.dtype), flags | (L.CONV_RELU if relu else 0),
                      int(bias_per_sample), ptr(src0), ptr(src1), ptr(weight), ptr(bias), ptr(residual), ptr(out),
-                     ptr(q), 0)
+                     ptr(q), 0, C.pointer(gn_bwd) if gn_bwd is not None else None)
     check(lib().pu_conv2d(C.byref(a), stream_ptr()), 'conv2d')
     return (out, q) if want_qstats else out
+
+
+def conv_tc_applies(x, C1, Cout):
+    """Mirror of conv_tc_applicable (csrc/conv_tc.cu): will pu_conv2d run the tcgen05 kernel for this input?"""
+    return (x.dtype == torch.bfloat16 and x.shape[3] % 64 == 0 and C1 % 64 == 0 and Cout % 64 == 0
+            and x.shape[2] >= 16 and x.shape[1] >= 8)
+
+
+def gn_bwd_epilogue(src0, stats, gamma, beta, src1=None, ada=None, silu=True, dropout_p=0.0, seed=0, eps=1e-5):
+    """Descriptor (PuConvGnBwd) that lets the data-gradient conv producing dL/dy of a GroupNorm(+SiLU)(+dropout) do the
+    first pass of the GroupNorm backward in its epilogue.  Returns (descriptor, sums, keepalive); pass the descriptor
+    to conv2d(gn_bwd=...) and `sums` to gn_bwd(..., sums=sums, du_ready=True)."""
+    N, H, W, C0 = _nhwc(src0)
+    C1 = src1.shape[3] if src1 is not None else 0
+    Cc = C0 + C1
+    consts = torch.empty((N, Cc, 4), dtype=torch.float32, device=src0.device)
+    f = _gn_args(src0, src1, stats, gamma, beta, ada, silu, L.RS_NONE, dropout_p, seed, None, eps)
+    check(lib().pu_gn_bwd_consts(C.byref(f), ptr(consts), stream_ptr()), 'gn_bwd_consts')
+    sums = torch.empty((N, Cc, 2), dtype=torch.float64, device=src0.device)
+    d = L.PuConvGnBwd(ptr(src0), ptr(src1), C0, C1, ptr(consts), ptr(sums), int(silu), float(dropout_p), int(seed))
+    return d, sums, consts
 
 
 def conv2d_wgrad(src0, dy, ksize, src1=None, dw=None, accumulate=False, flags=0):
@@ -210,7 +231,8 @@ def gn_apply(src0, stats, gamma, beta, src1=None, ada=None, silu=True, resample=
 
 def gn_bwd(src0, stats, gamma, beta, dy, dgamma, dbeta, src1=None, ada=None, dada=None, silu=True,
            resample=L.RS_NONE, dropout_p=0.0, seed=0, eps=1e-5, dres=None, dres_resample=L.RS_NONE,
-           dx0=None, dx1=None, acc0=False, acc1=False, acc_params=False, colsum0=None, colsum1=None):
+           dx0=None, dx1=None, acc0=False, acc1=False, acc_params=False, colsum0=None, colsum1=None, sums=None,
+           du_ready=False):
     """Returns (dx0, dx1).  dgamma/dbeta/dada are written (or accumulated into when acc_params).
     colsum0 / colsum1 (optional fp32 [C0] / [C1]) receive the per-channel sums of the final dx0 / dx1."""
     N, H, W, C0 = _nhwc(src0)
@@ -221,10 +243,12 @@ def gn_bwd(src0, stats, gamma, beta, dy, dgamma, dbeta, src1=None, ada=None, dad
     if src1 is not None and dx1 is None:
         dx1 = torch.empty_like(src1)
         acc1 = False
-    sums = torch.empty((N, C0 + C1, 2), dtype=torch.float64, device=src0.device)
+    if sums is None:
+        assert not du_ready
+        sums = torch.empty((N, C0 + C1, 2), dtype=torch.float64, device=src0.device)
     f = _gn_args(src0, src1, stats, gamma, beta, ada, silu, resample, dropout_p, seed, None, eps)
     a = L.PuGnBwdArgs(f, ptr(dy), ptr(dres), dres_resample, ptr(sums), ptr(dx0), ptr(dx1), int(acc0), int(acc1),
-                      ptr(dgamma), ptr(dbeta), ptr(dada), int(acc_params), ptr(colsum0), ptr(colsum1))
+                      ptr(dgamma), ptr(dbeta), ptr(dada), int(acc_params), ptr(colsum0), ptr(colsum1), int(du_ready))
     check(lib().pu_gn_bwd(C.byref(a), stream_ptr()), 'gn_bwd')
     return dx0, dx1
 

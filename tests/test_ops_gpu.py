@@ -333,6 +333,76 @@ def test_groupnorm_fwd_bwd(case, dtype):
         assert rel_err(dada, ada.grad) < btol
 
 
+GNB_CASES = [
+    # N, H, W, C0, C1 (channels of the normalised x), Co (channels of the conv after the norm), k, silu, ada, dropout
+    (2, 16, 16, 128, 0, 128, 3, True, True, 0.1),     # norm1 -> dropout -> conv1
+    (1, 16, 32, 256, 128, 256, 3, True, False, 0.0),  # norm0 over a concatenation -> conv0
+    (2, 16, 16, 256, 0, 768, 1, False, False, 0.0),   # norm2 -> qkv 1x1 (no SiLU)
+    (1, 24, 40, 128, 0, 64, 3, True, False, 0.0),     # out_norm -> out_conv, partial tiles
+    (2, 32, 32, 64, 64, 192, 3, True, True, 0.25),
+]
+
+
+@pytest.mark.parametrize('case', GNB_CASES)
+def test_conv_dgrad_groupnorm_backward_epilogue(case):
+    """pu_conv2d with PuConvArgs.gn_bwd: the data-gradient conv's epilogue does the first pass of the GroupNorm backward
+    (dropout mask, SiLU derivative, per-(sample, channel) sums) and pu_gn_bwd(du_ready=1) only its second pass.  Must
+    agree with the unfused sequence (dgrad conv, then the two-pass pu_gn_bwd) and, without dropout, with autograd."""
+    N, H, W, C0, C1, Co, k, silu, use_ada, p = case
+    dt = torch.bfloat16
+    Cc = C0 + C1
+    x = (rnd(N, Cc, H, W, seed=1) * 1.5 + 0.3).to(dt).float().requires_grad_(True)
+    gamma = (1 + 0.1 * rnd(Cc, seed=2)).requires_grad_(True)
+    beta = (0.1 * rnd(Cc, seed=3)).requires_grad_(True)
+    ada = (0.1 * rnd(2 * Cc, seed=4)).requires_grad_(True) if use_ada else None
+    w = (rnd(Co, Cc, k, k, seed=7) / math.sqrt(Cc * k * k)).to(dt).float()
+    dyo = rnd(N, Co, H, W, seed=5).to(dt).float()            # gradient wrt the conv output
+    dres = rnd(N, Cc, H, W, seed=6).to(dt).float()
+    xs = nhwc(x.detach(), dt)
+    s0 = xs[..., :C0].contiguous()
+    s1 = xs[..., C0:].contiguous() if C1 else None
+    stats = ops.gn_stats(s0, s1)
+    adad = ada.detach() if use_ada else None
+    wd = ops.pack_weight(w, 1, dt)
+    kw = dict(src1=s1, ada=adad, silu=silu, dropout_p=p, seed=4321)
+
+    def run(fused):
+        dg, db = torch.empty(Cc, device=DEV), torch.empty(Cc, device=DEV)
+        dada = torch.empty(2 * Cc, device=DEV) if use_ada else None
+        cs0 = torch.empty(C0, device=DEV)
+        cs1 = torch.empty(C1, device=DEV) if C1 else None
+        if fused:
+            d, sums, _ = ops.gn_bwd_epilogue(s0, stats, gamma.detach(), beta.detach(), **kw)
+            du = ops.conv2d(nhwc(dyo, dt), wd, Cc, k, gn_bwd=d, flags=L.CONV_FORCE_TC)
+            dx0, dx1 = ops.gn_bwd(s0, stats, gamma.detach(), beta.detach(), du, dg, db, dada=dada, dres=nhwc(dres, dt),
+                                  colsum0=cs0, colsum1=cs1, sums=sums, du_ready=True, **kw)
+        else:
+            dh = ops.conv2d(nhwc(dyo, dt), wd, Cc, k, flags=L.CONV_FORCE_TC)
+            dx0, dx1 = ops.gn_bwd(s0, stats, gamma.detach(), beta.detach(), dh, dg, db, dada=dada, dres=nhwc(dres, dt),
+                                  colsum0=cs0, colsum1=cs1, **kw)
+        dx = torch.cat([dx0, dx1], dim=-1) if C1 else dx0
+        return dx.float(), dg, db, dada, cs0
+
+    fa, ua = run(True), run(False)
+    names = ('dx', 'dgamma', 'dbeta', 'dada', 'colsum')
+    for name, a, b in zip(names, fa, ua):
+        if a is None:
+            continue
+        e = rel_err(a, b)
+        print(f'gn-bwd epilogue {case} {name}: fused vs unfused rel {e:.3e}')
+        assert e < 1e-2, (name, e)          # the unfused path rounds dL/dh to bf16 before the SiLU derivative
+    if p == 0.0:
+        y = _gn_ref(x, gamma, beta, ada, silu, 0)
+        F.conv2d(y, w, padding=k // 2).backward(dyo)
+        assert rel_err(nchw(fa[0]), x.grad + dres) < 1.5e-2
+        assert rel_err(fa[1], gamma.grad) < 1.5e-2
+        assert rel_err(fa[2], beta.grad) < 1.5e-2
+        if use_ada:
+            assert rel_err(fa[3], ada.grad) < 1.5e-2
+        # the fused path skips one bf16 rounding, so it must not be further from autograd than the unfused one (+10 %)
+        assert rel_err(nchw(fa[0]), x.grad + dres) <= 1.1 * rel_err(nchw(ua[0]), x.grad + dres) + 1e-4
+
+
 def test_groupnorm_dropout_consistency():
     N, H, W, Cc = 2, 8, 8, 128
     x = nhwc(rnd(N, Cc, H, W, seed=1), torch.float32)
