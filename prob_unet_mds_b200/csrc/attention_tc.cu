@@ -561,12 +561,6 @@ int attention_fwd_tc(const void* qkv, void* out, float* lse, int N, int T, int h
 //   dQ_i = dS K_j                                        (dS K-major, K_j MN-major)    -> TMEM -> red.add.v4 (fp32)
 // dQ partial sums of the different key tiles are combined with vectorised fp32 reductions into dq_acc [N*T][C].
 // ------------------------------------------------------------------------------------------------
-constexpr int AB_QD_STAGES = 2;
-constexpr int AB_DQ_ROW = (AT_D + 4) * 4;     // fp32 dQ staging row: 64 floats + 16 B pad (bank-conflict-free v4 stores)
-constexpr int AB_DQ_BYTES = AT_TQ * AB_DQ_ROW;
-constexpr int AB_SMEM = 2 * AT_TILE /*K,V*/ + AB_QD_STAGES * 2 * AT_TILE /*Q,dO*/ + 2 * AT_TILE /*P*/ + 2 * AT_TILE /*dS*/ +
-                        AB_DQ_BYTES + 1024 + 256;
-
 struct AttnBwdParams {
     int T, heads, C;
     const float* lse;
@@ -579,264 +573,25 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-__global__ void __launch_bounds__(384, 1)
-attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                   const AttnBwdParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sK = smem;
-    uint8_t* sV = sK + AT_TILE;
-    uint8_t* sQD = sV + AT_TILE;                           // stage s: Q at +s*2*TILE, dO at +s*2*TILE + TILE
-    uint8_t* sP = sQD + AB_QD_STAGES * 2 * AT_TILE;        // two 64-key blocks of [128 q][128 B]
-    uint8_t* sDS = sP + 2 * AT_TILE;
-    uint8_t* sDQ = sDS + 2 * AT_TILE;                      // fp32 [128][64 + 4] staging for the bulk reduction
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sDQ + AB_DQ_BYTES);
-    uint64_t* kv_full = bars;
-    uint64_t* qd_full = bars + 1;                          // [2]
-    uint64_t* qd_empty = qd_full + AB_QD_STAGES;
-    uint64_t* sdp_full = qd_empty + AB_QD_STAGES;
-    uint64_t* pds_full = sdp_full + 1;
-    uint64_t* dq_full = pds_full + 1;
-    uint64_t* dq_empty = dq_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_empty + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nh = blockIdx.y, n = nh / p.heads, h = nh % p.heads;
-    const int k0 = blockIdx.x * AT_TK;
-    const int nq = p.T / AT_TQ;
-    const int row_base = n * p.T;
-    const int colQ = h * AT_D, colK = p.C + h * AT_D, colV = 2 * p.C + h * AT_D;
-
-    if (warp == 0 && lane == 0) {
-        prefetch_tmap(&tmQKV);
-        prefetch_tmap(&tmDO);
-    }
-    if (warp == 1 && lane == 0) {
-        mbar_init(smem_u32(kv_full), 1);
-        for (int s = 0; s < AB_QD_STAGES; ++s) {
-            mbar_init(smem_u32(&qd_full[s]), 1);
-            mbar_init(smem_u32(&qd_empty[s]), 1);
-        }
-        mbar_init(smem_u32(sdp_full), 1);
-        mbar_init(smem_u32(pds_full), 8);    // one arrive per softmax warp (2 warpgroups x 4 warps)
-        mbar_init(smem_u32(dq_full), 1);
-        mbar_init(smem_u32(dq_empty), 8);
-        fence_barrier_init();
-    }
-    if (warp == 2) {
-        tmem_alloc(smem_u32(tmem_slot), 512);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
-    const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320,
-                   tDQ = tmem_base + 384;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            mbar_expect_tx(smem_u32(kv_full), 2 * AT_TILE);
-            tma_load_2d(smem_u32(sK), &tmQKV, smem_u32(kv_full), colK, row_base + k0);
-            tma_load_2d(smem_u32(sV), &tmQKV, smem_u32(kv_full), colV, row_base + k0);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int i = 0; i < nq; ++i) {
-                mbar_wait(smem_u32(&qd_empty[stage]), phase ^ 1);
-                const uint32_t fb = smem_u32(&qd_full[stage]);
-                mbar_expect_tx(fb, 2 * AT_TILE);
-                // q tiles are walked starting at this CTA's own key-tile index: concurrently running CTAs of one
-                // (sample, head) then reduce into different dQ tiles instead of contending for the same addresses
-                const int qi = (i + (int)blockIdx.x) % nq;
-                tma_load_2d(smem_u32(sQD + stage * 2 * AT_TILE), &tmQKV, fb, colQ, row_base + qi * AT_TQ);
-                tma_load_2d(smem_u32(sQD + stage * 2 * AT_TILE + AT_TILE), &tmDO, fb, colQ, row_base + qi * AT_TQ);
-                if (++stage == AB_QD_STAGES) {
-                    stage = 0;
-                    phase ^= 1;
-                }
-            }
-        }
-    } else if (warp == 1) {
-        {   // whole warp, warp-uniform control flow; mma_f16_ss / mma_commit elect one lane internally
-            constexpr uint32_t IDESC_S = idesc_bf16_f32(128, 128, 0, 0);     // S, dP
-            constexpr uint32_t IDESC_T = idesc_bf16_f32(128, 64, 1, 1);      // dV, dK (both operands MN-major)
-            constexpr uint32_t IDESC_Q = idesc_bf16_f32(128, 64, 0, 1);      // dQ
-            const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
-            const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
-            mbar_wait(smem_u32(kv_full), 0);
-            auto issue_sdp = [&](int stage) {
-                const uint32_t q_addr = smem_u32(sQD + stage * 2 * AT_TILE);
-                const uint32_t do_addr = q_addr + AT_TILE;
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    mma_f16_ss(tS, smem_desc_sw128(q_addr + k * 32, 16, 1024), smem_desc_sw128(k_addr + k * 32, 16, 1024),
-                               IDESC_S, k ? 1u : 0u);
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    mma_f16_ss(tDP, smem_desc_sw128(do_addr + k * 32, 16, 1024),
-                               smem_desc_sw128(v_addr + k * 32, 16, 1024), IDESC_S, k ? 1u : 0u);
-                mma_commit(smem_u32(sdp_full));
-            };
-            int stage = 0;
-            uint32_t phase = 0;
-            mbar_wait(smem_u32(&qd_full[0]), 0);
-            tc_fence_after();
-            issue_sdp(0);
-            for (int i = 0; i < nq; ++i) {
-                mbar_wait(smem_u32(pds_full), i & 1);
-                mbar_wait(smem_u32(dq_empty), (i & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t q_addr = smem_u32(sQD + stage * 2 * AT_TILE);
-                const uint32_t do_addr = q_addr + AT_TILE;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {   // K = 128 query rows, 16 per step
-                    mma_f16_ss(tDV, smem_desc_sw128(p_addr + k * 2048, AT_TILE, 1024),
-                               smem_desc_sw128(do_addr + k * 2048, AT_TILE, 1024), IDESC_T, (i | k) ? 1u : 0u);
-                }
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    mma_f16_ss(tDK, smem_desc_sw128(ds_addr + k * 2048, AT_TILE, 1024),
-                               smem_desc_sw128(q_addr + k * 2048, AT_TILE, 1024), IDESC_T, (i | k) ? 1u : 0u);
-                }
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {   // K = 128 keys: two 64-key blocks x four 16-key steps
-                    mma_f16_ss(tDQ, smem_desc_sw128(ds_addr + (k >> 2) * AT_TILE + (k & 3) * 32, 16, 1024),
-                               smem_desc_sw128(k_addr + k * 2048, AT_TILE, 1024), IDESC_Q, k ? 1u : 0u);
-                }
-                mma_commit(smem_u32(dq_full));
-                mma_commit(smem_u32(&qd_empty[stage]));
-                if (++stage == AB_QD_STAGES) {
-                    stage = 0;
-                    phase ^= 1;
-                }
-                if (i + 1 < nq) {
-                    mbar_wait(smem_u32(&qd_full[stage]), phase);
-                    tc_fence_after();
-                    issue_sdp(stage);
-                }
-            }
-        }
-    } else if (warp >= 4) {
-        // two softmax warpgroups (warps 4-7 and 8-11): both own query row r = TMEM lane r, warpgroup wg handles the
-        // 64-key block wg of S / dP (= shared-memory block wg of P / dS) and columns [32*wg, 32*wg+32) of dQ, dK, dV
-        const int q = warp & 3;
-        const int wg = (warp - 4) >> 2;
-        const int r = q * 32 + lane;
-        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-        const float sc = 0.125f * 1.4426950408889634f;
-        const float* lse = p.lse + ((long long)n * p.heads + h) * p.T;
-        const float* delta = p.delta + ((long long)n * p.heads + h) * p.T;
-        for (int i = 0; i < nq; ++i) {
-            const int qi = (i + (int)blockIdx.x) % nq;     // same rotation as the TMA producer
-            const float l2 = lse[qi * AT_TQ + r] * 1.4426950408889634f;
-            const float dl = delta[qi * AT_TQ + r];
-            mbar_wait(smem_u32(sdp_full), i & 1);
-            tc_fence_after();
-#pragma unroll 1
-            for (int c = wg * 64; c < wg * 64 + 64; c += 32) {
-                uint32_t sv[32], dv[32];
-                tmem_ld32(tS + lane_off + c, sv);
-                tmem_ld32(tDP + lane_off + c, dv);
-                tc_wait_ld();
-                uint8_t* pb = sP + (c >> 6) * AT_TILE + r * 128;
-                uint8_t* db = sDS + (c >> 6) * AT_TILE + r * 128;
-                const int chunk0 = (c & 63) >> 3;
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    uint4 pk, dk;
-                    __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&pk);
-                    __nv_bfloat162* hd = reinterpret_cast<__nv_bfloat162*>(&dk);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int i0 = g * 8 + 2 * e;
-                        const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i0]), sc, -l2));
-                        const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i0 + 1]), sc, -l2));
-                        const float d0 = p0 * (__uint_as_float(dv[i0]) - dl) * 0.125f;
-                        const float d1 = p1 * (__uint_as_float(dv[i0 + 1]) - dl) * 0.125f;
-                        hp[e] = __floats2bfloat162_rn(p0, p1);
-                        hd[e] = __floats2bfloat162_rn(d0, d1);
-                    }
-                    const int off = ((chunk0 + g) ^ (r & 7)) << 4;
-                    *reinterpret_cast<uint4*>(pb + off) = pk;
-                    *reinterpret_cast<uint4*>(db + off) = dk;
-                }
-            }
-            tc_fence_before();
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(pds_full));
-            // dQ_i partial -> fp32 reduction
-            mbar_wait(smem_u32(dq_full), i & 1);
-            tc_fence_after();
-            float* dst = p.dq_acc + ((long long)row_base + qi * AT_TQ + r) * p.C + h * AT_D;
-            {
-                // TMEM -> registers -> this thread's 128-byte half row of the fp32 staging tile -> one bulk
-                // reduce-add (TMA engine, fp32 atomics at L2) instead of 8 red.global.add.v4 instructions
-                const int c = wg * 32;
-                uint32_t v[32];
-                tmem_ld32(tDQ + lane_off + c, v);
-                // the previous trip's bulk reduction must have finished reading the staging row
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                tc_wait_ld();
-                uint8_t* srow = sDQ + r * AB_DQ_ROW + c * 4;
-#pragma unroll
-                for (int e = 0; e < 32; e += 4)
-                    *reinterpret_cast<uint4*>(srow + e * 4) = make_uint4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-                fence_proxy_async();
-                asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], 128;" ::"l"(dst + c),
-                             "r"(smem_u32(srow))
-                             : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(dq_empty));
-        }
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all dQ reductions of this thread have landed
-        // the last dq_full commit also covers the final dV / dK accumulation
-        __nv_bfloat16* kp = p.dqkv + ((long long)row_base + k0 + r) * 3 * p.C + colK;
-        __nv_bfloat16* vp = p.dqkv + ((long long)row_base + k0 + r) * 3 * p.C + colV;
-        {
-            const int c = wg * 32;
-            uint32_t a[32], b[32];
-            tmem_ld32(tDK + lane_off + c, a);
-            tmem_ld32(tDV + lane_off + c, b);
-            tc_wait_ld();
-#pragma unroll
-            for (int e = 0; e < 32; e += 16) {
-                float ka[16], va[16];
-#pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                    ka[u] = __uint_as_float(a[e + u]);
-                    va[u] = __uint_as_float(b[e + u]);
-                }
-                st16(kp + c + e, ka);
-                st16(vp + c + e, va);
-            }
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 2) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
-// backward, pipelined variant.  Same math and TMEM map as attn_bwd_tc_kernel, but S / dP are produced as two
-// 64-key halves with their own barriers and P / dS live in two shared-memory buffers (tile parity), so the tensor
-// pipe always runs one unit ahead of the softmax warps:
+// backward kernel.  S / dP are produced as two 64-key halves with their own barriers and P / dS live in two
+// shared-memory buffers (tile parity), so the tensor pipe always runs one unit ahead of the softmax warps:
 //   MMA warp, tile i :  [P/dS half 0 ready] dQ_i  = dS_h0 K_h0 ; S/dP half 0 of tile i+1
 //                       [P/dS half 1 ready] dQ_i += dS_h1 K_h1 ; dV += P^T dO ; dK += dS^T Q ; S/dP half 1 of tile i+1
-//   softmax warps    :  half 0 of tile i ; dQ_{i-1} -> fp32 reductions ; half 1 of tile i
-// The softmax warps never wait for an MMA that was not issued at least half a tile earlier.
+//   softmax warps    :  half 0 of tile i ; half 1 of tile i            (warps 4-11, nothing else)
+//   dQ drain warps   :  dQ_i : TMEM -> registers -> red.global.add.v4.f32   (warps 12-15, double-buffered accumulator)
+// The softmax warps never wait for an MMA that was not issued at least half a tile earlier.  The dQ partials used to be
+// drained by the softmax warps themselves between the two halves; the 32 KB of fp32 reductions per tile (bound by the
+// L2 atomic rate, ~1500 clk per tile and SM) then sat on the critical path next to the ~2000 clk of softmax work.  With
+// their own warpgroup and two dQ accumulators in the 64 spare TMEM columns, reductions, softmax and MMAs overlap.
+// TMEM map (512 columns): S 0-127 | dP 128-255 | dV 256-319 | dK 320-383 | dQ[0] 384-447 | dQ[1] 448-511.
 // ------------------------------------------------------------------------------------------------
 constexpr int AB2_SMEM = 2 * AT_TILE /*K,V*/ + 2 * 2 * AT_TILE /*Q,dO x2 stages*/ + 2 * 2 * AT_TILE /*P x2*/ +
                          2 * 2 * AT_TILE /*dS x2*/ + 1024 + 256;
 
-__global__ void __launch_bounds__(384, 1)
+constexpr int AB2_THREADS = 512;
+
+__global__ void __launch_bounds__(AB2_THREADS, 1)
 attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                     const AttnBwdParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -853,9 +608,10 @@ attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     uint64_t* sdp_full = qd_empty + 2;                     // [2] per key half
     uint64_t* pds_full = sdp_full + 2;                     // [2] per key half
     uint64_t* pds_free = pds_full + 2;                     // [2] per P/dS buffer
-    uint64_t* dq_full = pds_free + 2;
-    uint64_t* dq_empty = dq_full + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_empty + 1);
+    uint64_t* dq_full = pds_free + 2;                      // [2] per dQ accumulator
+    uint64_t* dq_empty = dq_full + 2;                      // [2]
+    uint64_t* fin = dq_empty + 2;                          // every MMA of the CTA has completed (dK / dV final)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fin + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nh = blockIdx.y, n = nh / p.heads, h = nh % p.heads;
@@ -876,9 +632,10 @@ attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             mbar_init(smem_u32(&sdp_full[s]), 1);
             mbar_init(smem_u32(&pds_full[s]), 8);    // one arrive per softmax warp
             mbar_init(smem_u32(&pds_free[s]), 1);
+            mbar_init(smem_u32(&dq_full[s]), 1);
+            mbar_init(smem_u32(&dq_empty[s]), 4);    // one arrive per drain warp
         }
-        mbar_init(smem_u32(dq_full), 1);
-        mbar_init(smem_u32(dq_empty), 8);
+        mbar_init(smem_u32(fin), 1);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -939,13 +696,14 @@ attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             const uint32_t q_addr = smem_u32(sQD + stage * 2 * AT_TILE);
             const uint32_t do_addr = q_addr + AT_TILE;
             const uint32_t p_addr = smem_u32(sP + stage * 2 * AT_TILE), ds_addr = smem_u32(sDS + stage * 2 * AT_TILE);
+            const uint32_t tDQb = tDQ + (uint32_t)(i & 1) * 64;      // dQ accumulator of this tile
             // ---- key half 0 ----
             mbar_wait(smem_u32(&pds_full[0]), i & 1);
-            if (i > 0) mbar_wait(smem_u32(dq_empty), (i - 1) & 1);
+            if (i >= 2) mbar_wait(smem_u32(&dq_empty[i & 1]), ((i >> 1) - 1) & 1);   // tile i-2 drained from this buffer
             tc_fence_after();
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                mma_f16_ss(tDQ, smem_desc_sw128(ds_addr + k * 32, 16, 1024),
+                mma_f16_ss(tDQb, smem_desc_sw128(ds_addr + k * 32, 16, 1024),
                            smem_desc_sw128(k_addr + k * 2048, AT_TILE, 1024), IDESC_Q, k ? 1u : 0u);
             if (i + 1 < nq) {
                 mbar_wait(smem_u32(&qd_full[stage ^ 1]), ((i + 1) >> 1) & 1);
@@ -957,7 +715,7 @@ attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             tc_fence_after();
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                mma_f16_ss(tDQ, smem_desc_sw128(ds_addr + AT_TILE + k * 32, 16, 1024),
+                mma_f16_ss(tDQb, smem_desc_sw128(ds_addr + AT_TILE + k * 32, 16, 1024),
                            smem_desc_sw128(k_addr + (4 + k) * 2048, AT_TILE, 1024), IDESC_Q, 1u);
 #pragma unroll
             for (int k = 0; k < 8; ++k)     // K = 128 query rows, 16 per step
@@ -967,10 +725,40 @@ attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             for (int k = 0; k < 8; ++k)
                 mma_f16_ss(tDK, smem_desc_sw128(ds_addr + k * 2048, AT_TILE, 1024),
                            smem_desc_sw128(q_addr + k * 2048, AT_TILE, 1024), IDESC_T, (i | k) ? 1u : 0u);
-            mma_commit(smem_u32(dq_full));
+            mma_commit(smem_u32(&dq_full[i & 1]));
             mma_commit(smem_u32(&qd_empty[stage]));
             mma_commit(smem_u32(&pds_free[stage]));
             if (i + 1 < nq) issue_sdp(stage ^ 1, 1);
+        }
+        mma_commit(smem_u32(fin));
+    } else if (warp >= 12) {
+        // dQ drain warpgroup: warp quadrant q owns query rows (= TMEM lanes) [32q, 32q+32), all 64 feature columns.
+        // dQ partial of tile i: TMEM -> registers -> vectorised fp32 reductions at L2 (bulk reductions by the TMA engine
+        // and fragment-layout loads were measured and did not help: the L2 atomic rate is the limit either way).
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        for (int i = 0; i < nq; ++i) {
+            const int b = i & 1;
+            const int qi = (i + (int)blockIdx.x) % nq;     // same rotation as the TMA producer
+            mbar_wait(smem_u32(&dq_full[b]), (i >> 1) & 1);
+            tc_fence_after();
+            uint32_t v0[32], v1[32];
+            tmem_ld32(tDQ + b * 64 + lane_off, v0);
+            tmem_ld32(tDQ + b * 64 + lane_off + 32, v1);
+            tc_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&dq_empty[b]));
+            float* dst = p.dq_acc + ((long long)row_base + qi * AT_TQ + r) * p.C + h * AT_D;
+#pragma unroll
+            for (int e = 0; e < 32; e += 4)
+                red_add_v4(dst + e, __uint_as_float(v0[e]), __uint_as_float(v0[e + 1]), __uint_as_float(v0[e + 2]),
+                           __uint_as_float(v0[e + 3]));
+#pragma unroll
+            for (int e = 0; e < 32; e += 4)
+                red_add_v4(dst + 32 + e, __uint_as_float(v1[e]), __uint_as_float(v1[e + 1]), __uint_as_float(v1[e + 2]),
+                           __uint_as_float(v1[e + 3]));
         }
     } else if (warp >= 4) {
         // eight softmax warps: warp quadrant q owns query rows (= TMEM lanes) [32q, 32q+32); within a 64-key half
@@ -1021,37 +809,16 @@ attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&pds_full[half]));
         };
-        // dQ partial of tile i: TMEM -> registers -> vectorised fp32 reductions at L2.  (Measured alternatives that did
-        // not help: bulk reductions by the TMA engine from a staging tile, fragment-layout loads so that each warp
-        // instruction covers full 32-byte sectors, spreading the reductions over the next unit.  The reductions cost
-        // ~1.4 ms of a 4.8 ms T=4096 call whichever way they are issued: L2 atomic throughput.)
-        auto dq_out = [&](int i) {
-            const int qi = (i + (int)blockIdx.x) % nq;
-            mbar_wait(smem_u32(dq_full), i & 1);
-            tc_fence_after();
-            const int c = wg * 32;
-            uint32_t v[32];
-            tmem_ld32(tDQ + lane_off + c, v);
-            tc_wait_ld();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(dq_empty));
-            float* dst = p.dq_acc + ((long long)row_base + qi * AT_TQ + r) * p.C + h * AT_D + c;
-#pragma unroll
-            for (int e = 0; e < 32; e += 4)
-                red_add_v4(dst + e, __uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]),
-                           __uint_as_float(v[e + 3]));
-        };
         for (int i = 0; i < nq; ++i) {
             const int qi = (i + (int)blockIdx.x) % nq;     // same rotation as the TMA producer
             l2 = lse[qi * AT_TQ + r] * 1.4426950408889634f;
             dl = delta[qi * AT_TQ + r];
             unit(i, 0);
-            if (i > 0) dq_out(i - 1);
             unit(i, 1);
         }
-        dq_out(nq - 1);
-        // the last dq_full commit also covers the final dV / dK accumulation
+        // final dV / dK: wait until every MMA of this CTA has completed
+        mbar_wait(smem_u32(fin), 0);
+        tc_fence_after();
         __nv_bfloat16* kp = p.dqkv + ((long long)row_base + k0 + r) * 3 * p.C + colK;
         __nv_bfloat16* vp = p.dqkv + ((long long)row_base + k0 + r) * 3 * p.C + colV;
         {
@@ -1106,20 +873,14 @@ int attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const 
     if (rc) return rc;
     rc = make_mat_tmap(&tmdo, dout, (long long)N * T, (long long)C, 128);
     if (rc) return rc;
-    PU_SMEM_ATTR(attn_bwd_tc_kernel, AB_SMEM);
     PU_CUDA(cudaMemsetAsync(dq_acc, 0, sizeof(float) * (size_t)N * T * C, st));
     AttnBwdParams p;
     p.T = T; p.heads = heads; p.C = C;
     p.lse = lse; p.delta = delta; p.dq_acc = dq_acc;
     p.dqkv = (__nv_bfloat16*)dqkv;
     dim3 grid(T / AT_TK, N * heads);
-    const char* ev = getenv("PU_ATTN_BWD");       // PU_ATTN_BWD=1 selects the unpipelined kernel (A/B measurements)
-    if (ev && ev[0] == '1') {
-        attn_bwd_tc_kernel<<<grid, 384, AB_SMEM, st>>>(tm, tmdo, p);
-    } else {
-        PU_SMEM_ATTR(attn_bwd_tc2_kernel, AB2_SMEM);
-        attn_bwd_tc2_kernel<<<grid, 384, AB2_SMEM, st>>>(tm, tmdo, p);
-    }
+    PU_SMEM_ATTR(attn_bwd_tc2_kernel, AB2_SMEM);
+    attn_bwd_tc2_kernel<<<grid, AB2_THREADS, AB2_SMEM, st>>>(tm, tmdo, p);
     rc = check_launch("attn_bwd_tc");
     if (rc) return rc;
     long long total = (long long)N * T * (C / 8);
