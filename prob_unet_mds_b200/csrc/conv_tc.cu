@@ -223,17 +223,19 @@ constexpr int A_BYTES = 128 * 128;          // 128 rows x 64 bf16
 // MT = number of 128-pixel accumulators per CTA tile.  MT = 2 (a 16x16-pixel tile, two TMA boxes sharing one weight
 // tile) is used for Cout tiles of <= 128 channels: those layers are bound by the L2 -> shared-memory operand traffic
 // (32 KB per 128x128x64 MMA block), and sharing B between two accumulators cuts it by a quarter per FLOP.
-template <int BN, int MT = 1>
+template <int BN, int MT = 1, bool GNB = false>
 struct ConvTcCfg {
     static constexpr int B_BYTES = BN * 128;
     static constexpr int A_STAGE = MT * A_BYTES;
-    static constexpr int MAX_STAGES = (227 * 1024 - 1280) / (A_STAGE + B_BYTES);
+    // GroupNorm-backward epilogue: per accumulator stage the tile's per-channel constants (float4) and sums (2 floats)
+    static constexpr int GNB_BYTES = GNB ? 2 * BN * (16 + 8) : 0;
+    static constexpr int MAX_STAGES = (227 * 1024 - 1280 - GNB_BYTES) / (A_STAGE + B_BYTES);
     static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
     static constexpr int ACC1 = (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
     static constexpr int ACC_STRIDE = MT * ACC1;          // one accumulator stage
     static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
     static_assert(TMEM_COLS <= 512, "two accumulator stages must fit the 512 TMEM columns");
-    static constexpr int SMEM = STAGES * (A_STAGE + B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int SMEM = STAGES * (A_STAGE + B_BYTES) + 1024 /*align*/ + 256 /*barriers*/ + GNB_BYTES;
 };
 
 // GNB = true: the epilogue is the GroupNorm-backward one (PuConvGnBwd) and nothing else (no bias / residual / ReLU)
@@ -241,7 +243,7 @@ template <int BN, int MT, bool GNB = false>
 __global__ void __launch_bounds__(384, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const ConvTcParams p) {
-    using Cfg = ConvTcCfg<BN, MT>;
+    using Cfg = ConvTcCfg<BN, MT, GNB>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int A_STAGE = Cfg::A_STAGE;
     constexpr int TH = TILE_H * MT;              // tile height in pixels
@@ -255,6 +257,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     uint64_t* tfull = bars + 2 * STAGES;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float4* gnb_consts = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2][BN]   (GNB only)
+    float* gnb_sums = reinterpret_cast<float*>(gnb_consts + 2 * BN);                          // [2][BN][2]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -375,6 +379,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const int r = q * 32 + lane;
             const float* bias = p.bias ? (p.bias + (p.bias_per_sample ? (long long)img * p.Cout : 0) + n0) : nullptr;
 
+            if constexpr (GNB) {
+                // the tile's per-channel constants -> shared memory, its channel sums zeroed (overlaps the tile's MMAs)
+                const int et = threadIdx.x - 128;
+                for (int cc = et; cc < BN; cc += 256) {
+                    gnb_consts[acc * BN + cc] = __ldg(p.gconsts + (long long)img * (p.gC0 + p.gC1) + n0 + cc);
+                    gnb_sums[(acc * BN + cc) * 2] = 0.f;
+                    gnb_sums[(acc * BN + cc) * 2 + 1] = 0.f;
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
             mbar_wait(smem_u32(&tfull[acc]), acc_phase);
             tc_fence_after();
 #pragma unroll 1
@@ -421,7 +435,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         keep = 0u;
                     }
                     const float inv_keep = p.gdrop > 0.f ? 1.f / (1.f - p.gdrop) : 1.f;
-                    const float4* kc = p.gconsts + (long long)img * Cn + ch0;
+                    const float4* kc = gnb_consts + acc * BN + c;        // (ag, bg, rstd, -mean * rstd) per channel
                     auto xval = [&](int j) {
                         const __nv_bfloat162 xx = *reinterpret_cast<const __nv_bfloat162*>(&xr[j >> 1]);
                         return (j & 1) ? __high2float(xx) : __low2float(xx);
@@ -430,7 +444,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     for (int j = 0; j < 32; ++j) {
                         float gg = ((keep >> j) & 1u) ? f[j] : 0.f;
                         if (p.gsilu) {
-                            const float2 k2 = __ldg(reinterpret_cast<const float2*>(kc + j));   // (ag, bg) of channel ch0 + j
+                            const float2 k2 = *reinterpret_cast<const float2*>(kc + j);         // (ag, bg) of channel ch0 + j
                             const float u = fmaf(xval(j), k2.x, k2.y);
                             const float s = sigmoid_fast(u);
                             gg *= (s * inv_keep) * fmaf(u, 1.f - s, 1.f);
@@ -451,13 +465,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                     }
                     // sum over the tile's pixels (lanes) of du * xhat and of du; lane l ends up with channel ch0 + l
                     const float sb = warp_reduce_scatter32([&](int j) {
-                        const float2 k2 = __ldg(reinterpret_cast<const float2*>(kc + j) + 1);      // (rstd, -mean * rstd)
+                        const float2 k2 = *(reinterpret_cast<const float2*>(kc + j) + 1);          // (rstd, -mean * rstd)
                         return f[j] * fmaf(xval(j), k2.x, k2.y);
                     }, lane);
                     const float sa = warp_reduce_scatter32([&](int j) { return f[j]; }, lane);
-                    double* sp = p.gsums + ((long long)img * Cn + ch0 + lane) * 2;
-                    atomicAdd(sp, (double)sa);
-                    atomicAdd(sp + 1, (double)sb);
+                    float* sp = gnb_sums + (acc * BN + c + lane) * 2;    // tile-level sums in shared memory (fp32) ...
+                    atomicAdd(sp, sa);
+                    atomicAdd(sp + 1, sb);
                 } else {
                 if (bias) {
 #pragma unroll
@@ -515,6 +529,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&tempty[acc]));
+            if constexpr (GNB) {
+                // ... flushed once per tile and channel with fp64 atomics (the sums over the whole image cancel heavily)
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const int et = threadIdx.x - 128;
+                for (int cc = et; cc < BN; cc += 256) {
+                    double* gp = p.gsums + ((long long)img * (p.gC0 + p.gC1) + n0 + cc) * 2;
+                    atomicAdd(gp, (double)gnb_sums[(acc * BN + cc) * 2]);
+                    atomicAdd(gp + 1, (double)gnb_sums[(acc * BN + cc) * 2 + 1]);
+                }
+            }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
@@ -1017,7 +1041,7 @@ static int conv_tc_launch_bn(const PuConvArgs* a, cudaStream_t st) {
     if constexpr (!GNB) {
         if (a->gn_bwd) return conv_tc_launch_bn<BN, MT, true>(a, st);
     }
-    using Cfg = ConvTcCfg<BN, MT>;
+    using Cfg = ConvTcCfg<BN, MT, GNB>;
     ConvTcParams p;
     p.N = a->N; p.H = a->H; p.W = a->W; p.Cout = a->Cout; p.ksize = a->ksize;
     p.cblk0 = a->C0 / 64;

@@ -83,10 +83,26 @@ def main():
         flops = 2.0 * B * hw * hw * co * k * k * (c0 + c1)
         t_f = timeit(lambda: ops.conv2d(x0, wf, co, k, bias=bias, src1=x1, flags=L.CONV_FORCE_TC))
         t_d = timeit(lambda: ops.conv2d(dy, wd, c0 + c1, k, flags=L.CONV_FORCE_TC))
+        # the same data gradient with the GroupNorm-backward epilogue (SiLU + dropout 0.1), and what it replaces: the
+        # first pass of pu_gn_bwd over the conv's output
+        Cn = c0 + c1
+        xn = torch.randn(B, hw, hw, Cn, device='cuda').to(dt)
+        gam, bet, ada = torch.ones(Cn, device='cuda'), torch.zeros(Cn, device='cuda'), torch.zeros(2 * Cn, device='cuda')
+        st = ops.gn_stats(xn)
+        d, sums, keep = ops.gn_bwd_epilogue(xn, st, gam, bet, ada=ada, silu=True, dropout_p=0.1, seed=1)
+        t_dg = timeit(lambda: ops.conv2d(dy, wd, Cn, k, flags=L.CONV_FORCE_TC, gn_bwd=d))
+        dh = ops.conv2d(dy, wd, Cn, k, flags=L.CONV_FORCE_TC)
+        dg_, db_, da_ = torch.empty(Cn, device='cuda'), torch.empty(Cn, device='cuda'), torch.empty(2 * Cn, device='cuda')
+        t_b2 = timeit(lambda: ops.gn_bwd(xn, st, gam, bet, dh, dg_, db_, ada=ada, dada=da_, silu=True, dropout_p=0.1, seed=1))
+        t_b1 = timeit(lambda: ops.gn_bwd(xn, st, gam, bet, dh, dg_, db_, ada=ada, dada=da_, silu=True, dropout_p=0.1, seed=1,
+                                         sums=sums, du_ready=True))
+        del xn, dh
         t_w = timeit(lambda: ops.conv2d_wgrad(x0, dy, k, src1=x1, flags=L.CONV_FORCE_TC))
         rows.append(dict(shape=f'{c0}+{c1}->{co} {hw}x{hw} k{k} x{cnt}', fwd_ms=round(t_f, 3), dgrad_ms=round(t_d, 3),
                          wgrad_ms=round(t_w, 3), fwd_tf=round(flops / t_f / 1e9, 1), dgrad_tf=round(flops / t_d / 1e9, 1),
-                         wgrad_tf=round(flops / t_w / 1e9, 1)))
+                         wgrad_tf=round(flops / t_w / 1e9, 1), dgrad_gnb_ms=round(t_dg, 3),
+                         gn_bwd_two_pass_ms=round(t_b2, 3), gn_bwd_second_pass_ms=round(t_b1, 3),
+                         gnb_gain_ms=round((t_d + t_b2) - (t_dg + t_b1), 3)))
         for key, t in (('fwd', t_f), ('dgrad', t_d), ('wgrad', t_w)):
             tot[key][0] += flops * cnt
             tot[key][1] += t * cnt
