@@ -99,6 +99,7 @@ typedef struct PuConvGnBwd {
     int silu;
     float dropout_p;
     unsigned long long seed;
+    const void* keep_mask; /* optional: the keep bits pu_gn_apply stored (PuGnArgs.keep_mask); NULL: Philox(seed, index) */
 } PuConvGnBwd;
 typedef struct PuConvArgs {
     int N, H, W;          /* output == input spatial size (stride 1, padding k/2)                     */
@@ -164,6 +165,9 @@ typedef struct PuGnArgs {
     const float* beta;    /* [C]                                                                       */
     const float* ada;     /* NULL or [2C] = (scale, shift) == affine.bias (networks.py:168-171)        */
     void* y;              /* NHWC [N,H',W',C]                                                          */
+    void* keep_mask;      /* optional uint8 [N*H*W*C/8], written by pu_gn_apply when dropout_p > 0: bit e of byte i */
+                          /* = element 8i+e of y is kept.  Lets the PuConvGnBwd epilogue read the mask (4 bytes per */
+                          /* 32 channels) instead of regenerating it with Philox; pu_gn_bwd itself regenerates it   */
 } PuGnArgs;
 int pu_gn_apply(const PuGnArgs* a, void* stream);
 

@@ -19,7 +19,7 @@ c_void_p, c_int, c_float, c_ll, c_ull = C.c_void_p, C.c_int, C.c_float, C.c_long
 
 class PuConvGnBwd(C.Structure):
     _fields_ = [('x0', c_void_p), ('x1', c_void_p), ('C0', c_int), ('C1', c_int), ('consts', c_void_p),
-                ('sums', c_void_p), ('silu', c_int), ('dropout_p', c_float), ('seed', c_ull)]
+                ('sums', c_void_p), ('silu', c_int), ('dropout_p', c_float), ('seed', c_ull), ('keep_mask', c_void_p)]
 
 
 class PuConvArgs(C.Structure):
@@ -40,7 +40,7 @@ class PuGnArgs(C.Structure):
     _fields_ = [('N', c_int), ('H', c_int), ('W', c_int), ('C0', c_int), ('C1', c_int), ('G', c_int),
                 ('dtype', c_int), ('silu', c_int), ('resample', c_int), ('eps', c_float), ('dropout_p', c_float),
                 ('seed', c_ull), ('src0', c_void_p), ('src1', c_void_p), ('stats', c_void_p), ('gamma', c_void_p),
-                ('beta', c_void_p), ('ada', c_void_p), ('y', c_void_p)]
+                ('beta', c_void_p), ('ada', c_void_p), ('y', c_void_p), ('keep_mask', c_void_p)]
 
 
 class PuGnBwdArgs(C.Structure):

@@ -55,7 +55,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __global__ void __launch_bounds__(256, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; an OFFSET from the
+    // __shared__ symbol, so that plain C++ accesses below compile to LDS / STS instead of generic LD / ST
     uint8_t* sQ = smem;
     uint8_t* sKV = sQ + AT_TILE;                              // stage s: K at +s*2*TILE, V at +s*2*TILE + TILE
     uint8_t* sP = sKV + AT_KV_STAGES * 2 * AT_TILE;           // buffer b at +b*2*TILE (two 64-key K-blocks)
@@ -286,7 +287,8 @@ constexpr int A2_SMEM = 2 * AT_TILE /*Q0,Q1*/ + A2_KV_STAGES * 2 * AT_TILE /*K,V
 __global__ void __launch_bounds__(384, 1)
 attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; an OFFSET from the
+    // __shared__ symbol, so that plain C++ accesses below compile to LDS / STS instead of generic LD / ST
     uint8_t* sQ = smem;                                        // q tile t at + t*TILE
     uint8_t* sKV = sQ + 2 * AT_TILE;                           // stage s: K at +s*2*TILE, V at +s*2*TILE + TILE
     uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + A2_KV_STAGES * 2 * AT_TILE);
@@ -595,7 +597,8 @@ __global__ void __launch_bounds__(AB2_THREADS, 1)
 attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                     const AttnBwdParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; an OFFSET from the
+    // __shared__ symbol, so that plain C++ accesses below compile to LDS / STS instead of generic LD / ST
     uint8_t* sK = smem;
     uint8_t* sV = sK + AT_TILE;
     uint8_t* sQD = sV + AT_TILE;                           // stage s: Q at +s*2*TILE, dO at +s*2*TILE + TILE

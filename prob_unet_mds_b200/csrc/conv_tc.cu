@@ -168,6 +168,7 @@ struct ConvTcParams {
     int gsilu;
     float gdrop;
     unsigned long long gseed;
+    const uint32_t* gmask;  // stored keep bits (one word per pixel and 32 channels) or nullptr
 };
 
 // Sums each of 16 per-lane values over the 32 lanes of the warp with 16 shuffles (recursive halving: at every step a
@@ -228,7 +229,9 @@ struct ConvTcCfg {
     static constexpr int B_BYTES = BN * 128;
     static constexpr int A_STAGE = MT * A_BYTES;
     // GroupNorm-backward epilogue: per accumulator stage the tile's per-channel constants (float4) and sums (2 floats)
-    static constexpr int GNB_BYTES = GNB ? 2 * BN * (16 + 8) : 0;
+    // plus a [32][17]-float transposition scratch per epilogue warp for the per-channel sums over the tile's pixels
+    static constexpr int GNB_SCRATCH = 32 * 17 * 4;
+    static constexpr int GNB_BYTES = GNB ? 2 * BN * (16 + 8) + 8 * GNB_SCRATCH : 0;
     static constexpr int MAX_STAGES = (227 * 1024 - 1280 - GNB_BYTES) / (A_STAGE + B_BYTES);
     static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
     static constexpr int ACC1 = (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
@@ -248,7 +251,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     constexpr int A_STAGE = Cfg::A_STAGE;
     constexpr int TH = TILE_H * MT;              // tile height in pixels
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; an OFFSET from the
+    // __shared__ symbol, so that plain C++ accesses below compile to LDS / STS instead of generic LD / ST
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_STAGE;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_BYTES);
@@ -259,6 +263,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     float4* gnb_consts = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2][BN]   (GNB only)
     float* gnb_sums = reinterpret_cast<float*>(gnb_consts + 2 * BN);                          // [2][BN][2]
+    float* gnb_scratch = gnb_sums + 2 * BN * 2;                                               // [8 warps][32][17]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -426,10 +431,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                                        "=r"(xr[14]), "=r"(xr[15])
                                      : "l"(xp + 16));
                         if (p.gdrop > 0.f) {
-                            keep = 0u;
-                            const unsigned long long e8 = (unsigned long long)((pix * Cn + ch0) >> 3);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) keep |= dropout_keep8(p.gseed, e8 + i, p.gdrop) << (8 * i);
+                            if (p.gmask) {
+                                keep = __ldg(p.gmask + ((pix * Cn + ch0) >> 5));      // the bits gn_apply stored
+                            } else {
+                                keep = 0u;
+                                const unsigned long long e8 = (unsigned long long)((pix * Cn + ch0) >> 3);
+#pragma unroll 1
+                                for (int i = 0; i < 4; ++i) keep |= dropout_keep8(p.gseed, e8 + i, p.gdrop) << (8 * i);
+                            }
                         }
                     } else {
                         keep = 0u;
@@ -463,15 +472,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                             st16(op + j, ov);
                         }
                     }
-                    // sum over the tile's pixels (lanes) of du * xhat and of du; lane l ends up with channel ch0 + l
-                    const float sb = warp_reduce_scatter32([&](int j) {
-                        const float2 k2 = *(reinterpret_cast<const float2*>(kc + j) + 1);          // (rstd, -mean * rstd)
-                        return f[j] * fmaf(xval(j), k2.x, k2.y);
-                    }, lane);
-                    const float sa = warp_reduce_scatter32([&](int j) { return f[j]; }, lane);
-                    float* sp = gnb_sums + (acc * BN + c + lane) * 2;    // tile-level sums in shared memory (fp32) ...
-                    atomicAdd(sp, sa);
-                    atomicAdd(sp + 1, sb);
+                    // sums over the tile's pixels (= lanes) of du and du * xhat, 16 channels at a time through a [32][17]
+                    // transposition scratch: every lane writes its row, then lane l adds up 16 rows of column l & 15
+                    // (conflict-free both ways; a shuffle butterfly needs ~3x the instructions and serialises on latency)
+                    float* scr = gnb_scratch + (warp - 4) * (32 * 17);
+                    float* sp = gnb_sums + (acc * BN + c) * 2;           // tile-level sums in shared memory (fp32) ...
+#pragma unroll
+                    for (int round = 0; round < 4; ++round) {
+                        const int j0 = (round & 1) * 16;
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) {
+                            float val = f[j0 + jj];
+                            if (round >= 2) {
+                                const float2 k2 = *(reinterpret_cast<const float2*>(kc + j0 + jj) + 1);   // (rstd, -mean*rstd)
+                                val *= fmaf(xval(j0 + jj), k2.x, k2.y);
+                            }
+                            scr[lane * 17 + jj] = val;
+                        }
+                        __syncwarp();
+                        const float* colp = scr + (lane >> 4) * (16 * 17) + (lane & 15);
+                        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                        for (int rr = 0; rr < 16; rr += 4) {
+                            s0 += colp[(rr + 0) * 17];
+                            s1 += colp[(rr + 1) * 17];
+                            s2 += colp[(rr + 2) * 17];
+                            s3 += colp[(rr + 3) * 17];
+                        }
+                        float tot = (s0 + s1) + (s2 + s3);
+                        tot += __shfl_xor_sync(0xffffffffu, tot, 16);
+                        __syncwarp();
+                        if (lane < 16) atomicAdd(sp + (j0 + lane) * 2 + (round >> 1), tot);
+                    }
                 } else {
                 if (bias) {
 #pragma unroll
@@ -586,7 +618,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
     constexpr int STAGES = Cfg::STAGES;
     constexpr int STAGE_BYTES = Cfg::A_BYTES_ + Cfg::B_BYTES_;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; an OFFSET from the
+    // __shared__ symbol, so that plain C++ accesses below compile to LDS / STS instead of generic LD / ST
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
     uint64_t* full = bars;
     uint64_t* empty = bars + STAGES;
@@ -803,7 +836,8 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant
     constexpr int A_BYTES2 = Cfg::A_SUBS * WG_SUB;
     constexpr int B_ONE = (BN / 64) * WG_SUB;      // one activation (B) operand
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned; an OFFSET from the
+    // __shared__ symbol, so that plain C++ accesses below compile to LDS / STS instead of generic LD / ST
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
     uint64_t* full = bars;
     uint64_t* empty = bars + STAGES;
@@ -1071,6 +1105,7 @@ static int conv_tc_launch_bn(const PuConvArgs* a, cudaStream_t st) {
         p.gsilu = g->silu;
         p.gdrop = g->dropout_p;
         p.gseed = g->seed;
+        p.gmask = (const uint32_t*)g->keep_mask;
     }
 
     CUtensorMap tA0, tA1, tB;

@@ -311,6 +311,7 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_apply_kernel(PuGnArgs f, int
                     const uint32_t keep = dropout_keep8(f.seed, (unsigned long long)((opix * C + c0) >> 3), f.dropout_p);
 #pragma unroll
                     for (int e = 0; e < 8; ++e) o[e] = ((keep >> e) & 1u) ? o[e] * inv_keep : 0.f;
+                    if (f.keep_mask) reinterpret_cast<uint8_t*>(f.keep_mask)[(opix * C + c0) >> 3] = (uint8_t)keep;
                 }
                 st8(y + (long long)rr * C, o);
             }
@@ -360,6 +361,7 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_apply_kernel(PuGnArgs f, int
             const uint32_t keep = dropout_keep8(f.seed, (unsigned long long)((opix * C + c0) >> 3), f.dropout_p);
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] = ((keep >> e) & 1u) ? o[e] * inv_keep : 0.f;
+            if (f.keep_mask) reinterpret_cast<uint8_t*>(f.keep_mask)[(opix * C + c0) >> 3] = (uint8_t)keep;
         }
         st8(y + (long long)op * C, o);
     }

@@ -148,6 +148,7 @@ class UNetEngine:
         # GroupNorm statistics come out of the producing convolutions' epilogues (per quad of channels); self._q maps an
         # activation tensor to them for its consumers (the next block's norm0, also across a skip concatenation)
         self._q = {}
+        self._prod = {}       # id(activation) -> bias parameter of the conv that produced it (training tape only)
         # (quads need group sizes that are multiples of 4: model_channels % 128 == 0 -- true for the Probabilistic U-Net's
         # backbone, not for the 64-channel deterministic baseline, whose 192-channel levels have groups of 6)
         self._fused_stats = (os.environ.get('PROBUNET_B200_FUSED_GN_STATS', '1') != '0'
@@ -163,6 +164,7 @@ class UNetEngine:
                 x = self._conv_q(xin, self.w_fwd(mod.weight, Ci_pad=xin.shape[3]), mod.out_channels, mod.kernel,
                                  bias=mod.bias)
                 rec = dict(kind='conv', mod=mod, xin=xin, out=x)
+                self._prod[id(x)] = mod.bias
             if save:
                 tape.append(rec)
             skips.append(x)
@@ -178,8 +180,9 @@ class UNetEngine:
         h = ops.gn_apply(x, st, u.out_norm.weight, u.out_norm.bias, silu=True, eps=u.out_norm.eps)
         feat = ops.conv2d(h, self.w_fwd(u.out_conv.weight), u.out_conv.out_channels, 3, bias=u.out_conv.bias)
         if save:
-            tape.append(dict(kind='out', x=x, st=st, h=h, out=feat))
+            tape.append(dict(kind='out', x=x, st=st, h=h, out=feat, bias_x=self._prod.get(id(x))))
         self._q = {}
+        self._prod = {}
         return feat, tape
 
     def _conv_q(self, *args, **kw):
@@ -208,8 +211,12 @@ class UNetEngine:
         a = self._conv_q(h0, self.w_fwd(blk.conv0.weight), Cout, 3, bias=blk.conv0.bias)
         st1 = self._stats(a)
         p = float(blk.dropout) if training else 0.0
+        # training: keep the dropout mask bits (1/16 of the activation's bytes) so that the data-gradient conv's
+        # GroupNorm-backward epilogue reads them instead of regenerating the mask (a third of its instructions)
+        mask1 = (torch.empty(a.numel() // 8, dtype=torch.uint8, device=a.device)
+                 if (save and p > 0.0 and a.shape[3] % 32 == 0) else None)
         h1 = ops.gn_apply(a, st1, blk.norm1.weight, blk.norm1.bias, ada=blk.affine.bias, silu=True, dropout_p=p,
-                          seed=seed, eps=blk.norm1.eps)
+                          seed=seed, eps=blk.norm1.eps, keep_mask=mask1)
         w1 = self.w_fwd(blk.conv1.weight)
         if blk.skip is not None and blk.skip.weight is not None:
             if blk.up or blk.down:
@@ -227,7 +234,7 @@ class UNetEngine:
         rec = None
         if save:
             rec = dict(kind='block', blk=blk, xa=xa, xb=xb, st0=st0, h0=h0, a=a, st1=st1, h1=h1, y=y, p=p, seed=seed,
-                       rs=rs)
+                       rs=rs, mask1=mask1, bias_xa=self._prod.get(id(xa)), bias_xb=self._prod.get(id(xb)) if xb is not None else None)
         out = y
         if blk.num_heads:
             heads = blk.num_heads
@@ -241,6 +248,7 @@ class UNetEngine:
                 rec.update(st2=st2, h2=h2, qkv=qkv, att=att, lse=lse, perm=perm)
         if save:
             rec['out'] = out
+            self._prod[id(out)] = blk.proj.bias if blk.num_heads else blk.conv1.bias
         return out, rec
 
     # ---- backward ---------------------------------------------------------------------------------------------------
@@ -281,13 +289,14 @@ class UNetEngine:
             torch.cuda.current_stream().wait_stream(self._side)
             self._side_used = False
 
-    def _dgrad_gn(self, dy, w, Cin, k, x0, st, norm, x1=None, ada=None, silu=True, p=0.0, seed=0, rs=L.RS_NONE):
+    def _dgrad_gn(self, dy, w, Cin, k, x0, st, norm, x1=None, ada=None, silu=True, p=0.0, seed=0, rs=L.RS_NONE,
+                  keep_mask=None):
         """Data gradient of a conv whose input was GroupNorm(+SiLU)(+dropout) of x0 (|| x1).  Where the tcgen05 kernel
         applies (and no resampling sits between the norm and the conv) its epilogue already does the first pass of the
         GroupNorm backward: it returns du = dL/du and the per-(sample, channel) sums; otherwise (dL/dh, None)."""
         if self._fused_gn_bwd and rs == L.RS_NONE and ops.conv_tc_applies(dy, 0, Cin):
             d, sums, _ = ops.gn_bwd_epilogue(x0, st, norm.weight, norm.bias, src1=x1, ada=ada, silu=silu, dropout_p=p,
-                                             seed=seed, eps=norm.eps)
+                                             seed=seed, eps=norm.eps, keep_mask=keep_mask)
             return ops.conv2d(dy, w, Cin, k, gn_bwd=d), sums
         return ops.conv2d(dy, w, Cin, k), None
 
@@ -302,13 +311,13 @@ class UNetEngine:
         rec = tape[-1]
         # order everywhere below: data gradient first, then the weight gradient (side stream, starts once the dgrad
         # has finished) so that it runs under the GroupNorm-backward kernels that follow on the main stream
-        grads[id(u.out_conv.bias)] = ops.bias_grad(dfeat)
+        grads[id(u.out_conv.bias)] = ops.bias_grad(dfeat, db=grads.alloc(u.out_conv.bias))
         dh, sums = self._dgrad_gn(dfeat, self.w_dgrad(u.out_conv.weight), rec['h'].shape[3], 3, rec['x'], rec['st'],
                                   u.out_norm)
         self._wgrad(grads, u.out_conv.weight, rec['h'], dfeat, 3)
-        dg = torch.empty_like(u.out_norm.weight)
-        db = torch.empty_like(u.out_norm.bias)
-        cs = torch.empty(rec['x'].shape[3], dtype=torch.float32, device=dh.device)
+        dg = grads.alloc(u.out_norm.weight)
+        db = grads.alloc(u.out_norm.bias)
+        cs = self._bias_buf(grads, rec.get('bias_x'), rec['x'].shape[3], dh.device)
         dx, _ = ops.gn_bwd(rec['x'], rec['st'], u.out_norm.weight, u.out_norm.bias, dh, dg, db, silu=True,
                            eps=u.out_norm.eps, colsum0=cs, sums=sums, du_ready=sums is not None)
         grads[id(u.out_norm.weight)] = dg
@@ -340,15 +349,15 @@ class UNetEngine:
             self._wgrad(grads, blk.proj.weight, rec['att'], dz, 1)
             dqkv = ops.attention_bwd(rec['qkv'], rec['att'], datt, rec['lse'], heads)
             dbq = ops.bias_grad(dqkv)
-            gq = torch.empty_like(blk.qkv.bias)
+            gq = grads.alloc(blk.qkv.bias)
             ops.scatter(dbq, perm, gq)
             grads[id(blk.qkv.bias)] = gq
             dh2, sums = self._dgrad_gn(dqkv, self.w_dgrad(blk.qkv.weight, perm), Cout, 1, rec['y'], rec['st2'], blk.norm2,
                                        silu=False)
             self._wgrad(grads, blk.qkv.weight, rec['h2'], dqkv, 1, perm=perm)
-            dg = torch.empty_like(blk.norm2.weight)
-            db = torch.empty_like(blk.norm2.bias)
-            cs = torch.empty(Cout, dtype=torch.float32, device=dz.device)
+            dg = grads.alloc(blk.norm2.weight)
+            db = grads.alloc(blk.norm2.bias)
+            cs = self._bias_buf(grads, blk.conv1.bias, Cout, dz.device)
             dy, _ = ops.gn_bwd(rec['y'], rec['st2'], blk.norm2.weight, blk.norm2.bias, dh2, dg, db, silu=False,
                                eps=blk.norm2.eps, dres=dz, colsum0=cs, sums=sums, du_ready=sums is not None)
             self._gsum[id(dy)] = cs
@@ -360,12 +369,12 @@ class UNetEngine:
         bias_dy = self._colsum(dy)
         grads[id(blk.conv1.bias)] = bias_dy
         dh1, sums = self._dgrad_gn(dy, self.w_dgrad(blk.conv1.weight), Cout, 3, rec['a'], rec['st1'], blk.norm1,
-                                   ada=blk.affine.bias, p=rec['p'], seed=rec['seed'])
+                                   ada=blk.affine.bias, p=rec['p'], seed=rec['seed'], keep_mask=rec.get('mask1'))
         self._wgrad(grads, blk.conv1.weight, rec['h1'], dy, 3)
-        dg = torch.empty_like(blk.norm1.weight)
-        db = torch.empty_like(blk.norm1.bias)
-        dada = torch.empty_like(blk.affine.bias)
-        cs = torch.empty(Cout, dtype=torch.float32, device=dy.device)
+        dg = grads.alloc(blk.norm1.weight)
+        db = grads.alloc(blk.norm1.bias)
+        dada = grads.alloc(blk.affine.bias)
+        cs = self._bias_buf(grads, blk.conv0.bias, Cout, dy.device)
         da, _ = ops.gn_bwd(rec['a'], rec['st1'], blk.norm1.weight, blk.norm1.bias, dh1, dg, db, ada=blk.affine.bias,
                            dada=dada, silu=True, dropout_p=rec['p'], seed=rec['seed'], eps=blk.norm1.eps, colsum0=cs,
                            sums=sums, du_ready=sums is not None)
@@ -378,7 +387,7 @@ class UNetEngine:
         dh0, sums0 = self._dgrad_gn(da, self.w_dgrad(blk.conv0.weight), Cin, 3, xa, rec['st0'], blk.norm0, x1=xb, rs=rs)
         # skip branch
         if blk.skip is not None and blk.skip.weight is not None:
-            grads[id(blk.skip.bias)] = ops.clone(bias_dy)   # same values as conv1.bias' gradient, own storage
+            grads[id(blk.skip.bias)] = ops.clone(bias_dy, out=grads.alloc(blk.skip.bias))   # same values as conv1.bias' gradient
             dres = ops.conv2d(dy, self.w_dgrad(blk.skip.weight), Cin, 1)
             dres_rs = L.RS_NONE
             self._wgrad(grads, blk.skip.weight, xa, dy, 1, src1=xb)
@@ -386,12 +395,12 @@ class UNetEngine:
             dres = dy
             dres_rs = rs
         self._wgrad(grads, blk.conv0.weight, rec['h0'], da, 3)
-        dg = torch.empty_like(blk.norm0.weight)
-        db = torch.empty_like(blk.norm0.bias)
+        dg = grads.alloc(blk.norm0.weight)
+        db = grads.alloc(blk.norm0.bias)
         ga = gbuf.get(id(xa))
         gb = gbuf.get(id(xb)) if xb is not None else None
-        csa = torch.empty(xa.shape[3], dtype=torch.float32, device=dy.device)
-        csb = torch.empty(xb.shape[3], dtype=torch.float32, device=dy.device) if xb is not None else None
+        csa = self._bias_buf(grads, rec.get('bias_xa'), xa.shape[3], dy.device)
+        csb = self._bias_buf(grads, rec.get('bias_xb'), xb.shape[3], dy.device) if xb is not None else None
         dxa, dxb = ops.gn_bwd(xa, rec['st0'], blk.norm0.weight, blk.norm0.bias, dh0, dg, db, src1=xb, silu=True,
                               resample=rs, eps=blk.norm0.eps, dres=dres, dres_resample=dres_rs,
                               dx0=ga, dx1=gb, acc0=ga is not None, acc1=gb is not None, colsum0=csa, colsum1=csb,
@@ -403,6 +412,15 @@ class UNetEngine:
         if xb is not None:
             gbuf[id(xb)] = dxb
             self._gsum[id(dxb)] = csb
+
+    @staticmethod
+    def _bias_buf(grads, bias_param, n, device):
+        """fp32 [n] buffer for the per-channel sums of a data gradient == the bias gradient of the conv that produced the
+        tensor: taken from the gradient sink (under data parallelism a view into an all-reduce bucket, no staging copy)
+        when that conv's bias parameter is known."""
+        if bias_param is not None and bias_param.numel() == n:
+            return grads.alloc(bias_param)
+        return torch.empty(n, dtype=torch.float32, device=device)
 
     def _colsum(self, g):
         """Per-channel sum of a gradient tensor: taken from the gn_bwd call that wrote it, else computed."""
@@ -535,13 +553,13 @@ class GaussianEngine:
         net = self.net
         convs = self.convs()
         m = tape['m']
-        gw = torch.empty_like(net.conv_mu.weight)
-        gb = torch.empty_like(net.conv_mu.bias)
+        gw = grads.alloc(net.conv_mu.weight)
+        gb = grads.alloc(net.conv_mu.bias)
         dm = ops.heads_bwd(m, net.conv_mu.weight, dmu, gw, gb)
         grads[id(net.conv_mu.weight)] = gw
         grads[id(net.conv_mu.bias)] = gb
-        gw = torch.empty_like(net.conv_log_sigma.weight)
-        gb = torch.empty_like(net.conv_log_sigma.bias)
+        gw = grads.alloc(net.conv_log_sigma.weight)
+        gb = grads.alloc(net.conv_log_sigma.bias)
         ops.heads_bwd(m, net.conv_log_sigma.weight, dls, gw, gb, dm=dm)
         grads[id(net.conv_log_sigma.weight)] = gw
         grads[id(net.conv_log_sigma.bias)] = gb
@@ -562,7 +580,7 @@ class GaussianEngine:
             g = grads.alloc(c.weight)
             ops.unpack_wgrad(dwp, g)
             grads[id(c.weight)] = g
-            grads[id(c.bias)] = ops.bias_grad(dr)
+            grads[id(c.bias)] = ops.bias_grad(dr, db=grads.alloc(c.bias))
             if i > 0:
                 dp = ops.conv2d(dr, self.w_dgrad(c.weight), c.in_channels, 3)
         return grads

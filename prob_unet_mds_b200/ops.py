@@ -23,9 +23,11 @@ def zeros(shape, dtype, device):
     return t
 
 
-def clone(t):
+def clone(t, out=None):
     assert t.is_contiguous()
-    out = torch.empty_like(t)
+    if out is None:
+        out = torch.empty_like(t)
+    assert out.is_contiguous() and out.numel() == t.numel() and out.dtype == t.dtype
     check(lib().pu_copy(ptr(out), ptr(t), t.numel() * t.element_size(), stream_ptr()), 'copy')
     return out
 
@@ -145,7 +147,8 @@ def conv_tc_applies(x, C1, Cout):
             and x.shape[2] >= 16 and x.shape[1] >= 8)
 
 
-def gn_bwd_epilogue(src0, stats, gamma, beta, src1=None, ada=None, silu=True, dropout_p=0.0, seed=0, eps=1e-5):
+def gn_bwd_epilogue(src0, stats, gamma, beta, src1=None, ada=None, silu=True, dropout_p=0.0, seed=0, eps=1e-5,
+                    keep_mask=None):
     """Descriptor (PuConvGnBwd) that lets the data-gradient conv producing dL/dy of a GroupNorm(+SiLU)(+dropout) do the
     first pass of the GroupNorm backward in its epilogue.  Returns (descriptor, sums, keepalive); pass the descriptor
     to conv2d(gn_bwd=...) and `sums` to gn_bwd(..., sums=sums, du_ready=True)."""
@@ -156,7 +159,8 @@ def gn_bwd_epilogue(src0, stats, gamma, beta, src1=None, ada=None, silu=True, dr
     f = _gn_args(src0, src1, stats, gamma, beta, ada, silu, L.RS_NONE, dropout_p, seed, None, eps)
     check(lib().pu_gn_bwd_consts(C.byref(f), ptr(consts), stream_ptr()), 'gn_bwd_consts')
     sums = torch.empty((N, Cc, 2), dtype=torch.float64, device=src0.device)
-    d = L.PuConvGnBwd(ptr(src0), ptr(src1), C0, C1, ptr(consts), ptr(sums), int(silu), float(dropout_p), int(seed))
+    d = L.PuConvGnBwd(ptr(src0), ptr(src1), C0, C1, ptr(consts), ptr(sums), int(silu), float(dropout_p), int(seed),
+                      ptr(keep_mask))
     return d, sums, consts
 
 
@@ -210,21 +214,22 @@ def gn_stats_from_quads(q0, q1=None, G=None):
     return stats
 
 
-def _gn_args(src0, src1, stats, gamma, beta, ada, silu, resample, dropout_p, seed, y, eps):
+def _gn_args(src0, src1, stats, gamma, beta, ada, silu, resample, dropout_p, seed, y, eps, keep_mask=None):
     N, H, W, C0 = _nhwc(src0)
     C1 = src1.shape[3] if src1 is not None else 0
     return L.PuGnArgs(N, H, W, C0, C1, stats.shape[1], dtype_code(src0.dtype), int(silu), resample, eps,
                       float(dropout_p), int(seed), ptr(src0), ptr(src1), ptr(stats), ptr(gamma), ptr(beta), ptr(ada),
-                      ptr(y))
+                      ptr(y), ptr(keep_mask))
 
 
 def gn_apply(src0, stats, gamma, beta, src1=None, ada=None, silu=True, resample=L.RS_NONE, dropout_p=0.0, seed=0,
-             eps=1e-5):
+             eps=1e-5, keep_mask=None):
+    """keep_mask: optional uint8 [N*H*W*C/8] that receives the dropout keep bits (for gn_bwd_epilogue)."""
     N, H, W, C0 = _nhwc(src0)
     Cc = C0 + (src1.shape[3] if src1 is not None else 0)
     OH, OW = (H * 2, W * 2) if resample == L.RS_UP else ((H // 2, W // 2) if resample == L.RS_DOWN else (H, W))
     y = torch.empty((N, OH, OW, Cc), dtype=src0.dtype, device=src0.device)
-    a = _gn_args(src0, src1, stats, gamma, beta, ada, silu, resample, dropout_p, seed, y, eps)
+    a = _gn_args(src0, src1, stats, gamma, beta, ada, silu, resample, dropout_p, seed, y, eps, keep_mask)
     check(lib().pu_gn_apply(C.byref(a), stream_ptr()), 'gn_apply')
     return y
 

@@ -315,22 +315,22 @@ class _ElboFunction(torch.autograd.Function):
         dlogits = ops.mse_fwd_bwd(s['out'], s['target'], scratch[0:1], dtype=dt, gscale=scales[0:1])
         feat, h1, h2 = s['feat'], s['h1'], s['h2']
         # layer 2: 64 -> num_classes
-        g = torch.empty_like(w2p)
+        g = grads.alloc(w2p)
         ops.unpack_wgrad(ops.conv2d_wgrad(h2, dlogits, 1), g)
         grads[id(w2p)] = g
-        grads[id(b2p)] = ops.bias_grad(dlogits)
+        grads[id(b2p)] = ops.bias_grad(dlogits, db=grads.alloc(b2p))
         dh2 = ops.conv2d(dlogits, ops.pack_weight(w2, 1, dt), 64, 1)
         dpre2 = ops.relu_mask(dh2, h2, out=dh2)
         # layer 1: 64 -> 64
-        g = torch.empty_like(w1p)
+        g = grads.alloc(w1p)
         ops.unpack_wgrad(ops.conv2d_wgrad(h1, dpre2, 1), g)
         grads[id(w1p)] = g
-        grads[id(b1p)] = ops.bias_grad(dpre2)
+        grads[id(b1p)] = ops.bias_grad(dpre2, db=grads.alloc(b1p))
         dh1 = ops.conv2d(dpre2, ops.pack_weight(w1, 1, dt), 64, 1)
         dpre1 = ops.relu_mask(dh1, h1, out=dh1)
         # layer 0: [feat ; z] -> 64, split into the feature half (a 1x1 conv) and the z half (per-sample bias)
-        g0 = torch.empty_like(w0p)
-        gb0 = torch.empty_like(b0p)
+        g0 = grads.alloc(w0p)
+        gb0 = grads.alloc(b0p)
         ops.unpack_wgrad(ops.conv2d_wgrad(feat, dpre1, 1), g0, Ci=64, dst_co_stride=64 + Lz)
         rmean = ops.global_mean(dpre1)
         dz = ops.fcomb_z_bwd(rmean, float(s['HW']), s['z'], w0, g0, gb0)

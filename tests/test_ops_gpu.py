@@ -374,13 +374,20 @@ def test_conv_dgrad_groupnorm_backward_epilogue(case):
     wd = ops.pack_weight(w, 1, dt)
     kw = dict(src1=s1, ada=adad, silu=silu, dropout_p=p, seed=4321)
 
-    def run(fused):
+    mask = None
+    if p > 0:       # the keep bits as pu_gn_apply stores them (PuGnArgs.keep_mask)
+        mask = torch.zeros(N * H * W * Cc // 8, dtype=torch.uint8, device=DEV)
+        ops.gn_apply(s0, stats, gamma.detach(), beta.detach(), keep_mask=mask, **kw)
+        frac = sum(bin(v).count('1') for v in mask.cpu().tolist()) / (mask.numel() * 8)
+        assert abs(frac - (1 - p)) < 0.02, frac
+
+    def run(fused, keep_mask=None):
         dg, db = torch.empty(Cc, device=DEV), torch.empty(Cc, device=DEV)
         dada = torch.empty(2 * Cc, device=DEV) if use_ada else None
         cs0 = torch.empty(C0, device=DEV)
         cs1 = torch.empty(C1, device=DEV) if C1 else None
         if fused:
-            d, sums, _ = ops.gn_bwd_epilogue(s0, stats, gamma.detach(), beta.detach(), **kw)
+            d, sums, _ = ops.gn_bwd_epilogue(s0, stats, gamma.detach(), beta.detach(), keep_mask=keep_mask, **kw)
             du = ops.conv2d(nhwc(dyo, dt), wd, Cc, k, gn_bwd=d, flags=L.CONV_FORCE_TC)
             dx0, dx1 = ops.gn_bwd(s0, stats, gamma.detach(), beta.detach(), du, dg, db, dada=dada, dres=nhwc(dres, dt),
                                   colsum0=cs0, colsum1=cs1, sums=sums, du_ready=True, **kw)
@@ -393,6 +400,10 @@ def test_conv_dgrad_groupnorm_backward_epilogue(case):
 
     fa, ua = run(True), run(False)
     names = ('dx', 'dgamma', 'dbeta', 'dada', 'colsum')
+    if mask is not None:        # stored mask == regenerated mask: same result up to the order of the fp32 atomics
+        for name, a, b in zip(names, run(True, keep_mask=mask), fa):
+            if a is not None:
+                assert rel_err(a, b) < 1e-5, ('stored mask', name, rel_err(a, b))
     for name, a, b in zip(names, fa, ua):
         if a is None:
             continue
