@@ -294,7 +294,10 @@ class UNetEngine:
         """Data gradient of a conv whose input was GroupNorm(+SiLU)(+dropout) of x0 (|| x1).  Where the tcgen05 kernel
         applies (and no resampling sits between the norm and the conv) its epilogue already does the first pass of the
         GroupNorm backward: it returns du = dL/du and the per-(sample, channel) sums; otherwise (dL/dh, None)."""
-        if self._fused_gn_bwd and rs == L.RS_NONE and ops.conv_tc_applies(dy, 0, Cin):
+        # The epilogue costs about as much as the pass it replaces, so it only pays where it hides behind the tile's MMAs:
+        # K = taps x channels of dy >= 2304 (measured per layer, scripts/bench_layers.py: 3x3 convs from >= 256 channels)
+        deep = k * k * dy.shape[3] >= 2304 or self._fused_gn_bwd_all
+        if self._fused_gn_bwd and deep and rs == L.RS_NONE and ops.conv_tc_applies(dy, 0, Cin):
             d, sums, _ = ops.gn_bwd_epilogue(x0, st, norm.weight, norm.bias, src1=x1, ada=ada, silu=silu, dropout_p=p,
                                              seed=seed, eps=norm.eps, keep_mask=keep_mask)
             return ops.conv2d(dy, w, Cin, k, gn_bwd=d), sums
@@ -303,7 +306,8 @@ class UNetEngine:
     def backward(self, tape, dfeat, grads):
         """dfeat: NHWC gradient wrt the features.  Fills grads[id(param)] for every live parameter."""
         u = self.unet
-        self._fused_gn_bwd = os.environ.get('PROBUNET_B200_FUSED_GN_BWD', '1') != '0'
+        self._fused_gn_bwd = os.environ.get('PROBUNET_B200_FUSED_GN_BWD', '1') != '0'       # 0: never, 1: where it pays,
+        self._fused_gn_bwd_all = os.environ.get('PROBUNET_B200_FUSED_GN_BWD', '1') == '2'   # 2: every eligible layer
         gbuf = {}   # id(activation tensor) -> gradient tensor accumulated so far
         self._gsum = {}   # id(gradient tensor) -> its per-channel sums (= bias gradient of the producing conv),
                           # emitted by the gn_bwd call that wrote the tensor last

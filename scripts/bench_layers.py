@@ -89,7 +89,9 @@ def main():
         xn = torch.randn(B, hw, hw, Cn, device='cuda').to(dt)
         gam, bet, ada = torch.ones(Cn, device='cuda'), torch.zeros(Cn, device='cuda'), torch.zeros(2 * Cn, device='cuda')
         st = ops.gn_stats(xn)
-        d, sums, keep = ops.gn_bwd_epilogue(xn, st, gam, bet, ada=ada, silu=True, dropout_p=0.1, seed=1)
+        mask = torch.empty(xn.numel() // 8, dtype=torch.uint8, device='cuda')     # keep bits as the forward stores them
+        ops.gn_apply(xn, st, gam, bet, ada=ada, silu=True, dropout_p=0.1, seed=1, keep_mask=mask)
+        d, sums, keep = ops.gn_bwd_epilogue(xn, st, gam, bet, ada=ada, silu=True, dropout_p=0.1, seed=1, keep_mask=mask)
         t_dg = timeit(lambda: ops.conv2d(dy, wd, Cn, k, flags=L.CONV_FORCE_TC, gn_bwd=d))
         dh = ops.conv2d(dy, wd, Cn, k, flags=L.CONV_FORCE_TC)
         dg_, db_, da_ = torch.empty(Cn, device='cuda'), torch.empty(Cn, device='cuda'), torch.empty(2 * Cn, device='cuda')

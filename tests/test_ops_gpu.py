@@ -271,6 +271,45 @@ def test_conv_wgrad(case, impl):
     assert rel_err(db, dy.sum(dim=(0, 2, 3))) < 1e-5
 
 
+_WGRAD_MODE_SNIPPET = r"""
+import math, sys, torch, torch.nn.functional as F
+sys.path.insert(0, {root!r})
+from prob_unet_mds_b200 import _lib as L, ops
+torch.backends.cudnn.allow_tf32 = False
+g = torch.Generator().manual_seed(0)
+worst = 0.0
+for (N, H, W, Ci, Co, k) in ((2, 32, 32, 128, 256, 3), (1, 24, 40, 128, 128, 3), (2, 16, 16, 256, 768, 1), (1, 64, 64, 64, 128, 3)):
+    x = torch.randn(N, Ci, H, W, generator=g).cuda().bfloat16().float()
+    dy = torch.randn(N, Co, H, W, generator=g).cuda().bfloat16().float()
+    w = torch.zeros(Co, Ci, k, k, device='cuda', requires_grad=True)
+    F.conv2d(x, w, padding=k // 2).backward(dy)
+    dwp = ops.conv2d_wgrad(x.permute(0, 2, 3, 1).contiguous().bfloat16(), dy.permute(0, 2, 3, 1).contiguous().bfloat16(), k,
+                           flags=L.CONV_FORCE_TC)
+    gw = torch.empty_like(w)
+    ops.unpack_wgrad(dwp, gw)
+    worst = max(worst, ((gw - w.grad).norm() / w.grad.norm()).item())
+print('WORST', worst)
+"""
+
+
+@pytest.mark.parametrize('mode', ['0', '1', '2', '3'])
+def test_wgrad_kernel_variants(mode):
+    """The weight-gradient kernel variants that the dispatcher does not pick by default (PU_WGRAD_MODE: 0 single
+    accumulator, 1 two Cout tiles, 2 two taps per CTA, 3 halo) stay selectable for A/B measurements; the switch is read once
+    per process, so each variant is checked against autograd in its own interpreter."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PU_WGRAD_MODE=mode)
+    r = subprocess.run([sys.executable, '-c', _WGRAD_MODE_SNIPPET.format(root=root)], capture_output=True, text=True,
+                       env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    worst = float(r.stdout.strip().split('WORST')[-1])
+    print(f'PU_WGRAD_MODE={mode}: worst rel err {worst:.3e}')
+    assert worst < 2e-3
+
+
 GN_CASES = [
     # N, H, W, C0, C1, silu, ada, resample, dropout
     (2, 8, 8, 128, 0, True, False, 0, 0.0),
@@ -403,7 +442,7 @@ def test_conv_dgrad_groupnorm_backward_epilogue(case):
     if mask is not None:        # stored mask == regenerated mask: same result up to the order of the fp32 atomics
         for name, a, b in zip(names, run(True, keep_mask=mask), fa):
             if a is not None:
-                assert rel_err(a, b) < 1e-5, ('stored mask', name, rel_err(a, b))
+                assert rel_err(a, b) < 1e-4, ('stored mask', name, rel_err(a, b))
     for name, a, b in zip(names, fa, ua):
         if a is None:
             continue
