@@ -10,6 +10,9 @@
 #include "../../include/probunet_b200.h"
 #include "common.cuh"
 #include "conv_internal.h"
+#include "tc_ptx.cuh"
+
+#include <stdlib.h>
 
 namespace pu {
 
@@ -737,6 +740,381 @@ __global__ void gn_bwd_params_kernel(PuGnBwdArgs a) {
     }
 }
 
+// ======================================================================================================================
+// Bulk-copy (TMA) staged variants of the three streaming kernels, bf16, no resampling.
+//
+// The register-pipelined kernels above keep ~2 rows x 16 B per array and thread in flight (24 - 50 KB per SM) and run at
+// 53 - 64 % of the measured copy bandwidth: Little's law at 6.5 TB/s x ~0.8 us wants >= 35 KB per SM *continuously* in
+// flight, and more loads per thread spill.  Here a producer warp streams the block's pixel range through a ring of
+// shared-memory stages with cp.async.bulk (1-D bulk copies: a pixel range of one sample is one contiguous run per source
+// tensor) -- 3 - 4 stages x 8 KB per input array, 2 blocks per SM -- and the 256 consumer threads keep the same
+// (channel-vector, pixel-lane) mapping and math as above, reading 16-byte vectors from shared memory (conflict-free: a
+// warp reads 512 contiguous bytes) and writing results straight to global memory.
+// ======================================================================================================================
+constexpr int GS_CONSUMERS = 256;
+constexpr int GS_THREADS = GS_CONSUMERS + 32;     // + one producer warp
+constexpr int GS_MAX_ARRAYS = 6;
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// One input array of a streamed kernel: `base` points at row r0 of the block's range, rows are row_bytes apart
+// (contiguous), and the array's tile sits at `off` bytes inside every stage.
+struct GsArray {
+    const uint8_t* base;
+    int row_bytes;
+    int off;
+};
+struct GsPlan {
+    GsArray arr[GS_MAX_ARRAYS];
+    int n_arrays;
+    int stage_bytes;      // multiple of 128
+    int stages;
+    int TR;               // rows per tile
+};
+
+// producer warp: fills stage (t % stages) with rows [t*TR, min((t+1)*TR, nrows)) of every array
+__device__ __forceinline__ void gs_produce(const GsPlan& pl, int nrows, uint8_t* stage0, uint64_t* full, uint64_t* empty) {
+    using namespace ptx;
+    if ((threadIdx.x & 31) != 0) return;
+    const int ntiles = cdiv(nrows, pl.TR);
+    for (int t = 0; t < ntiles; ++t) {
+        const int s = t % pl.stages;
+        const int use = t / pl.stages;
+        if (use > 0) mbar_wait(smem_u32(&empty[s]), (use - 1) & 1);
+        const int rows = min(pl.TR, nrows - t * pl.TR);
+        uint32_t total = 0;
+        for (int k = 0; k < pl.n_arrays; ++k) total += (uint32_t)(rows * pl.arr[k].row_bytes);
+        const uint32_t fb = smem_u32(&full[s]);
+        mbar_expect_tx(fb, total);
+        for (int k = 0; k < pl.n_arrays; ++k) {
+            if (pl.arr[k].row_bytes == 0) continue;            // unused slot
+            bulk_g2s(smem_u32(stage0 + (size_t)s * pl.stage_bytes + pl.arr[k].off),
+                     pl.arr[k].base + (size_t)t * pl.TR * pl.arr[k].row_bytes, (uint32_t)(rows * pl.arr[k].row_bytes), fb);
+        }
+    }
+}
+
+__device__ __forceinline__ Raw8<__nv_bfloat16> lds_raw(const uint8_t* p) {
+    Raw8<__nv_bfloat16> r;
+    r.v = *reinterpret_cast<const uint4*>(p);
+    return r;
+}
+
+// shared-memory carve-up common to the three kernels: [head bytes][barriers 2*stages][pad to 128][stages x stage_bytes]
+__device__ __forceinline__ void gs_carve(uint8_t* smem, int head_bytes, int stages, uint64_t*& full, uint64_t*& empty,
+                                         uint8_t*& stage0) {
+    full = reinterpret_cast<uint64_t*>(smem + ((head_bytes + 7) & ~7));
+    empty = full + stages;
+    const uint32_t bar_end = (uint32_t)(((head_bytes + 7) & ~7) + 2 * stages * 8);
+    stage0 = smem + ((bar_end + 127u) & ~127u);
+}
+__host__ __device__ inline int gs_smem_bytes(int head_bytes, int stages, int stage_bytes) {
+    return (((head_bytes + 7) & ~7) + 2 * stages * 8 + 127) / 128 * 128 + stages * stage_bytes + 128;
+}
+
+// ---- forward apply: y = dropout(act(x * ag + bg)) ----
+__global__ void __launch_bounds__(GS_THREADS, 2) gn_apply_tma_kernel(PuGnArgs f, int rows_per_block, GsPlan pl) {
+    using namespace ptx;
+    extern __shared__ uint8_t gs_raw[];
+    uint8_t* smem = gs_raw + ((128u - (smem_u32(gs_raw) & 127u)) & 127u);
+    uint64_t *full, *empty;
+    uint8_t* stage0;
+    gs_carve(smem, 0, pl.stages, full, empty, stage0);
+    const int C = f.C0 + f.C1, nvec = C / 8;
+    const int n = blockIdx.y;
+    const int HW = f.H * f.W;
+    const int r0 = blockIdx.x * rows_per_block;
+    const int nrows = min(rows_per_block, HW - r0);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < pl.stages; ++s) {
+            mbar_init(smem_u32(&full[s]), 1);
+            mbar_init(smem_u32(&empty[s]), GS_CONSUMERS / 32);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+    const long long in_base = (long long)n * HW + r0;
+    if (threadIdx.x >= GS_CONSUMERS) {
+        pl.arr[0].base = reinterpret_cast<const uint8_t*>(f.src0) + in_base * f.C0 * 2;
+        if (f.C1 > 0) pl.arr[1].base = reinterpret_cast<const uint8_t*>(f.src1) + in_base * f.C1 * 2;
+        gs_produce(pl, nrows, stage0, full, empty);
+        return;
+    }
+    const int PL = GS_CONSUMERS / nvec;
+    const int v = threadIdx.x % nvec, plane = threadIdx.x / nvec;
+    const bool active = plane < PL;
+    const int c0 = v * 8;
+    ChanConst k;
+    if (active) gn_load_consts(f, n, c0, k);
+    const float inv_keep = f.dropout_p > 0.f ? 1.f / (1.f - f.dropout_p) : 1.f;
+    __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(f.y) + in_base * C + c0;
+    const int xoff = (c0 < f.C0) ? pl.arr[0].off + c0 * 2 : pl.arr[1].off + (c0 - f.C0) * 2;
+    const int xrow = (c0 < f.C0) ? f.C0 * 2 : f.C1 * 2;
+    const int ntiles = cdiv(nrows, pl.TR);
+    for (int t = 0; t < ntiles; ++t) {
+        const int s = t % pl.stages;
+        mbar_wait(smem_u32(&full[s]), (t / pl.stages) & 1);
+        const uint8_t* st = stage0 + (size_t)s * pl.stage_bytes;
+        const int rows = min(pl.TR, nrows - t * pl.TR);
+        if (active) {
+            for (int rr = plane; rr < rows; rr += PL) {
+                float x[8], o[8];
+                unpack(lds_raw(st + xoff + rr * xrow), x);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float u = gn_u<true>(k, e, x[e]);
+                    o[e] = f.silu ? u * sigmoid_t<true>(u) : u;
+                }
+                const int row = t * pl.TR + rr;
+                if (f.dropout_p > 0.f) {
+                    const long long opix = in_base + row;
+                    const uint32_t keep = dropout_keep8(f.seed, (unsigned long long)((opix * C + c0) >> 3), f.dropout_p);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] = ((keep >> e) & 1u) ? o[e] * inv_keep : 0.f;
+                    if (f.keep_mask) reinterpret_cast<uint8_t*>(f.keep_mask)[(opix * C + c0) >> 3] = (uint8_t)keep;
+                }
+                st8(y + (long long)row * C, o);
+            }
+        }
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(smem_u32(&empty[s]));
+    }
+}
+
+// ---- backward, first pass: du (written over dy) and the per-(sample, channel) sums ----
+__global__ void __launch_bounds__(GS_THREADS, 2) gn_bwd_reduce_tma_kernel(PuGnBwdArgs a, int rows_per_block, GsPlan pl) {
+    using namespace ptx;
+    extern __shared__ uint8_t gs_raw[];
+    uint8_t* smem = gs_raw + ((128u - (smem_u32(gs_raw) & 127u)) & 127u);
+    const PuGnArgs& f = a.f;
+    const int C = f.C0 + f.C1, nvec = C / 8;
+    float* sm = reinterpret_cast<float*>(smem);                 // [C][2] block partial sums
+    uint64_t *full, *empty;
+    uint8_t* stage0;
+    gs_carve(smem, 2 * C * 4, pl.stages, full, empty, stage0);
+    const int n = blockIdx.y;
+    const int HW = f.H * f.W;
+    const int r0 = blockIdx.x * rows_per_block;
+    const int nrows = min(rows_per_block, HW - r0);
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < pl.stages; ++s) {
+            mbar_init(smem_u32(&full[s]), 1);
+            mbar_init(smem_u32(&empty[s]), GS_CONSUMERS / 32);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+    const long long in_base = (long long)n * HW + r0;
+    if (threadIdx.x >= GS_CONSUMERS) {
+        pl.arr[0].base = reinterpret_cast<const uint8_t*>(f.src0) + in_base * f.C0 * 2;
+        pl.arr[1].base = reinterpret_cast<const uint8_t*>(a.dy) + in_base * C * 2;
+        if (f.C1 > 0) pl.arr[2].base = reinterpret_cast<const uint8_t*>(f.src1) + in_base * f.C1 * 2;
+        gs_produce(pl, nrows, stage0, full, empty);
+    } else {
+        const int PL = GS_CONSUMERS / nvec;
+        const int v = threadIdx.x % nvec, plane = threadIdx.x / nvec;
+        const bool active = plane < PL;
+        const int c0 = v * 8;
+        ChanConst k;
+        if (active) gn_load_consts(f, n, c0, k);
+        float A[8], B[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) A[e] = B[e] = 0.f;
+        __nv_bfloat16* du_out = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(a.dy)) + in_base * C + c0;
+        const int xoff = (c0 < f.C0) ? pl.arr[0].off + c0 * 2 : pl.arr[2].off + (c0 - f.C0) * 2;
+        const int xrow = (c0 < f.C0) ? f.C0 * 2 : f.C1 * 2;
+        const int goff = pl.arr[1].off + c0 * 2;
+        const int ntiles = cdiv(nrows, pl.TR);
+        for (int t = 0; t < ntiles; ++t) {
+            const int s = t % pl.stages;
+            mbar_wait(smem_u32(&full[s]), (t / pl.stages) & 1);
+            const uint8_t* st = stage0 + (size_t)s * pl.stage_bytes;
+            const int rows = min(pl.TR, nrows - t * pl.TR);
+            if (active) {
+                for (int rr = plane; rr < rows; rr += PL) {
+                    float x[8], g[8], xh[8], du[8];
+                    unpack(lds_raw(st + xoff + rr * xrow), x);
+                    unpack(lds_raw(st + goff + rr * C * 2), g);
+                    const int row = t * pl.TR + rr;
+                    gn_du8_calc<true>(f, k, x, g, in_base + row, c0, xh, du);
+                    st8(du_out + (long long)row * C, du);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        A[e] += du[e];
+                        B[e] = fmaf(du[e], xh[e], B[e]);
+                    }
+                }
+            }
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) mbar_arrive(smem_u32(&empty[s]));
+        }
+        if (active) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                atomicAdd(&sm[2 * (c0 + e)], A[e]);
+                atomicAdd(&sm[2 * (c0 + e) + 1], B[e]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(a.sums + (long long)n * C * 2 + i, (double)sm[i]);
+}
+
+// ---- backward, second pass: dx = du * ag + s1 + xhat * s2 (+ dres) (+ old dx) ----
+__global__ void __launch_bounds__(GS_THREADS, 2) gn_bwd_apply_tma_kernel(PuGnBwdArgs a, int rows_per_block, GsPlan pl) {
+    using namespace ptx;
+    extern __shared__ uint8_t gs_raw[];
+    uint8_t* smem = gs_raw + ((128u - (smem_u32(gs_raw) & 127u)) & 127u);
+    const PuGnArgs& f = a.f;
+    const int C = f.C0 + f.C1, nvec = C / 8, Cg = C / f.G;
+    double* smd = reinterpret_cast<double*>(smem);              // [G][2]: sum_c gamma' A, sum_c gamma' B
+    float* csm = reinterpret_cast<float*>(smd + 2 * f.G);       // [C] column sums of the written gradient
+    uint64_t *full, *empty;
+    uint8_t* stage0;
+    gs_carve(smem, 2 * f.G * 8 + C * 4, pl.stages, full, empty, stage0);
+    const int n = blockIdx.y;
+    const int HW = f.H * f.W;
+    const int r0 = blockIdx.x * rows_per_block;
+    const int nrows = min(rows_per_block, HW - r0);
+    const bool want_cs = a.colsum0 != nullptr;
+    for (int i = threadIdx.x; i < 2 * f.G; i += blockDim.x) smd[i] = 0.0;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) csm[i] = 0.f;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < pl.stages; ++s) {
+            mbar_init(smem_u32(&full[s]), 1);
+            mbar_init(smem_u32(&empty[s]), GS_CONSUMERS / 32);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+    const long long in_base = (long long)n * HW + r0;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float gam = f.gamma[c];
+        if (f.ada) gam *= 1.f + f.ada[c];
+        const int g = c / Cg;
+        atomicAdd(&smd[2 * g], (double)gam * a.sums[((long long)n * C + c) * 2]);
+        atomicAdd(&smd[2 * g + 1], (double)gam * a.sums[((long long)n * C + c) * 2 + 1]);
+    }
+    __syncthreads();        // (before the role split: the producer loop blocks on the consumers' progress)
+    // array slots: 0 x0, 1 du, 2 x1, 3 dres, 4 old dx0, 5 old dx1 (unused slots have row_bytes 0 and are skipped)
+    if (threadIdx.x >= GS_CONSUMERS) {
+        pl.arr[0].base = reinterpret_cast<const uint8_t*>(f.src0) + in_base * f.C0 * 2;
+        pl.arr[1].base = reinterpret_cast<const uint8_t*>(a.dy) + in_base * C * 2;
+        pl.arr[2].base = reinterpret_cast<const uint8_t*>(f.src1) + in_base * f.C1 * 2;
+        pl.arr[3].base = reinterpret_cast<const uint8_t*>(a.dres) + in_base * C * 2;
+        pl.arr[4].base = reinterpret_cast<const uint8_t*>(a.dx0) + in_base * f.C0 * 2;
+        pl.arr[5].base = reinterpret_cast<const uint8_t*>(a.dx1) + in_base * f.C1 * 2;
+        gs_produce(pl, nrows, stage0, full, empty);
+    } else {
+        const int PL = GS_CONSUMERS / nvec;
+        const int v = threadIdx.x % nvec, plane = threadIdx.x / nvec;
+        const bool active = plane < PL;
+        const int c0 = v * 8;
+        ChanConst k;
+        float s1[8], s2[8], cs[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s1[e] = s2[e] = cs[e] = 0.f;
+        if (active) {
+            gn_load_consts(f, n, c0, k);
+            const double inv_m = 1.0 / ((double)Cg * (double)f.H * (double)f.W);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int g = (c0 + e) / Cg;
+                s1[e] = -k.rstd[e] * (float)(smd[2 * g] * inv_m);
+                s2[e] = -k.rstd[e] * (float)(smd[2 * g + 1] * inv_m);
+            }
+        }
+        const bool lo = c0 < f.C0;
+        const int xoff = lo ? pl.arr[0].off + c0 * 2 : pl.arr[2].off + (c0 - f.C0) * 2;
+        const int xrow = lo ? f.C0 * 2 : f.C1 * 2;
+        const int goff = pl.arr[1].off + c0 * 2;
+        const bool has_res = pl.arr[3].row_bytes != 0;
+        const int roff = pl.arr[3].off + c0 * 2;
+        const bool acc = lo ? (pl.arr[4].row_bytes != 0) : (pl.arr[5].row_bytes != 0);
+        const int ooff = lo ? pl.arr[4].off + c0 * 2 : pl.arr[5].off + (c0 - f.C0) * 2;
+        __nv_bfloat16* dst = lo ? reinterpret_cast<__nv_bfloat16*>(a.dx0) + in_base * f.C0 + c0
+                                : reinterpret_cast<__nv_bfloat16*>(a.dx1) + in_base * f.C1 + (c0 - f.C0);
+        const int dstride = lo ? f.C0 : f.C1;
+        const int ntiles = cdiv(nrows, pl.TR);
+        for (int t = 0; t < ntiles; ++t) {
+            const int s = t % pl.stages;
+            mbar_wait(smem_u32(&full[s]), (t / pl.stages) & 1);
+            const uint8_t* st = stage0 + (size_t)s * pl.stage_bytes;
+            const int rows = min(pl.TR, nrows - t * pl.TR);
+            if (active) {
+                for (int rr = plane; rr < rows; rr += PL) {
+                    float x[8], du[8], o[8];
+                    unpack(lds_raw(st + xoff + rr * xrow), x);
+                    unpack(lds_raw(st + goff + rr * C * 2), du);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float xh = gn_xhat<true>(k, e, x[e]);
+                        o[e] = fmaf(xh, s2[e], fmaf(du[e], k.ag[e], s1[e]));
+                    }
+                    if (has_res) {
+                        float d[8];
+                        unpack(lds_raw(st + roff + rr * C * 2), d);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) o[e] += d[e];
+                    }
+                    if (acc) {
+                        float old[8];
+                        unpack(lds_raw(st + ooff + rr * xrow), old);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) o[e] += old[e];
+                    }
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) cs[e] += o[e];
+                    st8(dst + (long long)(t * pl.TR + rr) * dstride, o);
+                }
+            }
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) mbar_arrive(smem_u32(&empty[s]));
+        }
+        if (want_cs && active) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) atomicAdd(&csm[c0 + e], cs[e]);
+        }
+    }
+    __syncthreads();
+    if (want_cs) {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            if (c < f.C0)
+                atomicAdd(a.colsum0 + c, csm[c]);
+            else if (a.colsum1)
+                atomicAdd(a.colsum1 + (c - f.C0), csm[c]);
+        }
+    }
+}
+
+// host: tile plan of a streamed launch.  row_bytes[i] == 0 marks an unused slot.
+static GsPlan gs_make_plan(int C, const int* row_bytes, int n_slots, int stages) {
+    GsPlan pl;
+    const int nvec = C / 8;
+    const int PL = GS_CONSUMERS / nvec;
+    pl.TR = 2 * (PL > 0 ? PL : 1);
+    pl.stages = stages;
+    pl.n_arrays = n_slots;
+    int off = 0;
+    for (int i = 0; i < GS_MAX_ARRAYS; ++i) {
+        pl.arr[i].base = nullptr;
+        pl.arr[i].row_bytes = i < n_slots ? row_bytes[i] : 0;
+        pl.arr[i].off = off;
+        off += ((pl.arr[i].row_bytes * pl.TR + 127) / 128) * 128;
+    }
+    pl.stage_bytes = off;
+    return pl;
+}
+static bool gs_enabled() {
+    static const bool on = !(getenv("PU_GN_TMA") && getenv("PU_GN_TMA")[0] == '0');
+    return on;
+}
+
 // the per-(sample, channel) constants of the conv epilogue that takes over the reduce pass (PuConvGnBwd.consts)
 __global__ void gn_bwd_consts_kernel(PuGnArgs f, float4* __restrict__ out) {
     const int C = f.C0 + f.C1;
@@ -846,6 +1224,17 @@ int pu_gn_apply(const PuGnArgs* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int C = a->C0 + a->C1;
     const int OHW = a->resample == PU_RS_UP ? a->H * a->W * 4 : (a->resample == PU_RS_DOWN ? a->H * a->W / 4 : a->H * a->W);
+    if (a->dtype == PU_BF16 && a->resample == PU_RS_NONE && gs_enabled()) {
+        const int rb[2] = {a->C0 * 2, a->C1 * 2};
+        GsPlan pl = gs_make_plan(C, rb, 2, 4);
+        const int rows = rows_per_block(OHW, a->N, pl.TR * 4, 2);
+        const int smem = gs_smem_bytes(0, pl.stages, pl.stage_bytes);
+        PU_SMEM_ATTR(gn_apply_tma_kernel, 100 * 1024);
+        PU_REQUIRE(smem <= 100 * 1024, "pu_gn_apply: tile plan needs %d bytes of shared memory", smem);
+        dim3 grid(cdiv(OHW, rows), a->N);
+        gn_apply_tma_kernel<<<grid, GS_THREADS, smem, st>>>(*a, rows, pl);
+        return check_launch("gn_apply_tma");
+    }
     const int PL = GN_THREADS / (C / 8);
     const int rows = rows_per_block(OHW, a->N, PL * 8);
     dim3 grid(cdiv(OHW, rows), a->N);
@@ -881,6 +1270,39 @@ int pu_gn_bwd(const PuGnBwdArgs* a, void* stream) {
     const int PL = GN_THREADS / (C / 8);
     const int rows = rows_per_block(HW, f.N, PL * 8, GN_BWD_BLOCKS);
     dim3 grid(cdiv(HW, rows), f.N);
+    const bool streamed = f.dtype == PU_BF16 && f.resample == PU_RS_NONE && (!a->dres || a->dres_resample == PU_RS_NONE) &&
+                          gs_enabled();
+    if (streamed) {
+        // bulk-copy staged kernels (see gn_apply_tma_kernel): same math, shared-memory ring fed by a producer warp
+        if (!a->du_ready) {
+            PU_CUDA(cudaMemsetAsync(a->sums, 0, sizeof(double) * 2 * f.N * C, st));
+            const int rb[3] = {f.C0 * 2, C * 2, f.C1 * 2};
+            GsPlan pl = gs_make_plan(C, rb, 3, 4);
+            const int rows1 = rows_per_block(HW, f.N, pl.TR * 4, 2);
+            const int smem = gs_smem_bytes(2 * C * 4, pl.stages, pl.stage_bytes);
+            PU_SMEM_ATTR(gn_bwd_reduce_tma_kernel, 110 * 1024);
+            PU_REQUIRE(smem <= 110 * 1024, "pu_gn_bwd: reduce tile plan needs %d bytes of shared memory", smem);
+            dim3 g1(cdiv(HW, rows1), f.N);
+            gn_bwd_reduce_tma_kernel<<<g1, GS_THREADS, smem, st>>>(*a, rows1, pl);
+            rc = check_launch("gn_bwd_reduce_tma");
+            if (rc) return rc;
+        }
+        if (a->colsum0) PU_CUDA(cudaMemsetAsync(a->colsum0, 0, sizeof(float) * f.C0, st));
+        if (a->colsum1 && f.C1 > 0) PU_CUDA(cudaMemsetAsync(a->colsum1, 0, sizeof(float) * f.C1, st));
+        const int rb[6] = {f.C0 * 2, C * 2, f.C1 * 2, a->dres ? C * 2 : 0, a->acc0 ? f.C0 * 2 : 0,
+                           (a->acc1 && f.C1 > 0) ? f.C1 * 2 : 0};
+        GsPlan pl = gs_make_plan(C, rb, 6, 3);
+        const int rows2 = rows_per_block(HW, f.N, pl.TR * 4, 2);
+        const int smem = gs_smem_bytes(2 * f.G * 8 + C * 4, pl.stages, pl.stage_bytes);
+        PU_SMEM_ATTR(gn_bwd_apply_tma_kernel, 110 * 1024);
+        PU_REQUIRE(smem <= 110 * 1024, "pu_gn_bwd: apply tile plan needs %d bytes of shared memory", smem);
+        dim3 g2(cdiv(HW, rows2), f.N);
+        gn_bwd_apply_tma_kernel<<<g2, GS_THREADS, smem, st>>>(*a, rows2, pl);
+        rc = check_launch("gn_bwd_apply_tma");
+        if (rc) return rc;
+        gn_bwd_params_kernel<<<cdiv(C, 128), 128, 0, st>>>(*a);
+        return check_launch("gn_bwd_params");
+    }
     if (!a->du_ready) {
         PU_CUDA(cudaMemsetAsync(a->sums, 0, sizeof(double) * 2 * f.N * C, st));
         const size_t smem = sizeof(float) * 2 * C;
