@@ -463,6 +463,15 @@ def bench_det_unet(ctx, args):
         opt.step()
     steps = max(2, min(args.steps, 5))
     ms = ctx.timed(step, steps, 2)
+    kinds = {}
+    if args.profile_calls and ctx.rank == 0:
+        from prob_unet_mds_b200 import _lib as L
+        prof = L.start_profiling()
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        L.stop_profiling()
+        kinds = {k: round(v['ms'] / 2, 3) for k, v in sorted(prof.summary().items(), key=lambda kv: -kv[1]['ms'])[:10]}
     peaks = measured_peaks()
     sps = Bd * ctx.world / (ms / 1e3)
     tf = GFLOP_DET_FWD_BWD_PER_SAMPLE * sps / 1e3
@@ -470,6 +479,7 @@ def bench_det_unet(ctx, args):
     torch.cuda.empty_cache()
     return {'metric': 'det_unet_train_samples_per_s', 'value': sps, 'unit': 'samples/s', 'ms_per_step': ms, 'steps': steps,
             'step_tflops_algorithmic': tf, 'step_frac_of_bf16_peak': tf / ctx.world / peaks['tflops_sustained'],
+            'kernel_ms_per_step': kinds,
             'config': {'model': 'baseline/deterministic_unet.UNet (22.8 M parameters)', 'per_gpu_batch': Bd, 'tile': Hd,
                        'loss': 'MSELoss(mean)', 'optimizer': 'prob_unet_mds_b200.AdamW', 'dtype': 'bf16',
                        'gflop_per_sample_fwd_bwd': GFLOP_DET_FWD_BWD_PER_SAMPLE}}

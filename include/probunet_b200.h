@@ -167,7 +167,7 @@ typedef struct PuGnArgs {
     void* y;              /* NHWC [N,H',W',C]                                                          */
     void* keep_mask;      /* optional uint8 [N*H*W*C/8], written by pu_gn_apply when dropout_p > 0: bit e of byte i */
                           /* = element 8i+e of y is kept.  Lets the PuConvGnBwd epilogue read the mask (4 bytes per */
-                          /* 32 channels) instead of regenerating it with Philox; pu_gn_bwd itself regenerates it   */
+                          /* 32 channels) instead of regenerating it with Philox; pu_gn_bwd reads it too when given */
 } PuGnArgs;
 int pu_gn_apply(const PuGnArgs* a, void* stream);
 

@@ -422,7 +422,9 @@ __device__ __forceinline__ void gn_du8_calc(const PuGnArgs& f, const ChanConst& 
     uint32_t keep = 0xffu;
     float inv_keep = 1.f;
     if (f.dropout_p > 0.f) {
-        keep = dropout_keep8(f.seed, (unsigned long long)((pix * C + c0) >> 3), f.dropout_p);
+        // the keep bits the forward stored (PuGnArgs.keep_mask), else regenerated from (seed, element index)
+        keep = f.keep_mask ? (uint32_t) reinterpret_cast<const uint8_t*>(f.keep_mask)[(pix * C + c0) >> 3]
+                           : dropout_keep8(f.seed, (unsigned long long)((pix * C + c0) >> 3), f.dropout_p);
         inv_keep = 1.f / (1.f - f.dropout_p);
     }
 #pragma unroll
@@ -741,15 +743,18 @@ __global__ void gn_bwd_params_kernel(PuGnBwdArgs a) {
 }
 
 // ======================================================================================================================
-// Bulk-copy (TMA) staged variants of the three streaming kernels, bf16, no resampling.
+// Bulk-copy (TMA) staged variants of the two backward passes, bf16, no resampling.
 //
-// The register-pipelined kernels above keep ~2 rows x 16 B per array and thread in flight (24 - 50 KB per SM) and run at
-// 53 - 64 % of the measured copy bandwidth: Little's law at 6.5 TB/s x ~0.8 us wants >= 35 KB per SM *continuously* in
-// flight, and more loads per thread spill.  Here a producer warp streams the block's pixel range through a ring of
-// shared-memory stages with cp.async.bulk (1-D bulk copies: a pixel range of one sample is one contiguous run per source
-// tensor) -- 3 - 4 stages x 8 KB per input array, 2 blocks per SM -- and the 256 consumer threads keep the same
-// (channel-vector, pixel-lane) mapping and math as above, reading 16-byte vectors from shared memory (conflict-free: a
-// warp reads 512 contiguous bytes) and writing results straight to global memory.
+// The register-pipelined kernels above keep ~2 rows x 16 B per array and thread in flight and run at 53 - 64 % of the
+// measured copy bandwidth.  Here a producer warp streams the block's pixel range through a ring of shared-memory stages
+// with cp.async.bulk (1-D bulk copies: a pixel range of one sample is one contiguous run per source tensor) -- 3 - 4
+// stages x 8 KB per input array, 2 blocks per SM -- and the 256 consumer threads keep the same (channel-vector,
+// pixel-lane) mapping and math as above, reading 16-byte vectors from shared memory (conflict-free: a warp reads 512
+// contiguous bytes) and writing results straight to global memory.  Measured (B200, batch 64): backward 0.445 -> 0.402 ms
+// at 128 channels x 128x128, 0.253 -> 0.232 at 256 x 64x64, i.e. ~10 %, not the 40 % a pure bandwidth model promised:
+// with 100+ instructions per 8 elements (sigmoid, mask, fp32 <-> bf16) these passes are as much issue- as HBM-bound.
+// The forward apply was 15 % SLOWER this way (two blocks of 8 consumer warps hide less latency than three blocks of the
+// register-pipelined kernel) and keeps the kernel above.
 // ======================================================================================================================
 constexpr int GS_CONSUMERS = 256;
 constexpr int GS_THREADS = GS_CONSUMERS + 32;     // + one producer warp
@@ -814,75 +819,6 @@ __device__ __forceinline__ void gs_carve(uint8_t* smem, int head_bytes, int stag
 }
 __host__ __device__ inline int gs_smem_bytes(int head_bytes, int stages, int stage_bytes) {
     return (((head_bytes + 7) & ~7) + 2 * stages * 8 + 127) / 128 * 128 + stages * stage_bytes + 128;
-}
-
-// ---- forward apply: y = dropout(act(x * ag + bg)) ----
-__global__ void __launch_bounds__(GS_THREADS, 2) gn_apply_tma_kernel(PuGnArgs f, int rows_per_block, GsPlan pl) {
-    using namespace ptx;
-    extern __shared__ uint8_t gs_raw[];
-    uint8_t* smem = gs_raw + ((128u - (smem_u32(gs_raw) & 127u)) & 127u);
-    uint64_t *full, *empty;
-    uint8_t* stage0;
-    gs_carve(smem, 0, pl.stages, full, empty, stage0);
-    const int C = f.C0 + f.C1, nvec = C / 8;
-    const int n = blockIdx.y;
-    const int HW = f.H * f.W;
-    const int r0 = blockIdx.x * rows_per_block;
-    const int nrows = min(rows_per_block, HW - r0);
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < pl.stages; ++s) {
-            mbar_init(smem_u32(&full[s]), 1);
-            mbar_init(smem_u32(&empty[s]), GS_CONSUMERS / 32);
-        }
-        fence_barrier_init();
-    }
-    __syncthreads();
-    const long long in_base = (long long)n * HW + r0;
-    if (threadIdx.x >= GS_CONSUMERS) {
-        pl.arr[0].base = reinterpret_cast<const uint8_t*>(f.src0) + in_base * f.C0 * 2;
-        if (f.C1 > 0) pl.arr[1].base = reinterpret_cast<const uint8_t*>(f.src1) + in_base * f.C1 * 2;
-        gs_produce(pl, nrows, stage0, full, empty);
-        return;
-    }
-    const int PL = GS_CONSUMERS / nvec;
-    const int v = threadIdx.x % nvec, plane = threadIdx.x / nvec;
-    const bool active = plane < PL;
-    const int c0 = v * 8;
-    ChanConst k;
-    if (active) gn_load_consts(f, n, c0, k);
-    const float inv_keep = f.dropout_p > 0.f ? 1.f / (1.f - f.dropout_p) : 1.f;
-    __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(f.y) + in_base * C + c0;
-    const int xoff = (c0 < f.C0) ? pl.arr[0].off + c0 * 2 : pl.arr[1].off + (c0 - f.C0) * 2;
-    const int xrow = (c0 < f.C0) ? f.C0 * 2 : f.C1 * 2;
-    const int ntiles = cdiv(nrows, pl.TR);
-    for (int t = 0; t < ntiles; ++t) {
-        const int s = t % pl.stages;
-        mbar_wait(smem_u32(&full[s]), (t / pl.stages) & 1);
-        const uint8_t* st = stage0 + (size_t)s * pl.stage_bytes;
-        const int rows = min(pl.TR, nrows - t * pl.TR);
-        if (active) {
-            for (int rr = plane; rr < rows; rr += PL) {
-                float x[8], o[8];
-                unpack(lds_raw(st + xoff + rr * xrow), x);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const float u = gn_u<true>(k, e, x[e]);
-                    o[e] = f.silu ? u * sigmoid_t<true>(u) : u;
-                }
-                const int row = t * pl.TR + rr;
-                if (f.dropout_p > 0.f) {
-                    const long long opix = in_base + row;
-                    const uint32_t keep = dropout_keep8(f.seed, (unsigned long long)((opix * C + c0) >> 3), f.dropout_p);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) o[e] = ((keep >> e) & 1u) ? o[e] * inv_keep : 0.f;
-                    if (f.keep_mask) reinterpret_cast<uint8_t*>(f.keep_mask)[(opix * C + c0) >> 3] = (uint8_t)keep;
-                }
-                st8(y + (long long)row * C, o);
-            }
-        }
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) mbar_arrive(smem_u32(&empty[s]));
-    }
 }
 
 // ---- backward, first pass: du (written over dy) and the per-(sample, channel) sums ----
@@ -1224,17 +1160,6 @@ int pu_gn_apply(const PuGnArgs* a, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int C = a->C0 + a->C1;
     const int OHW = a->resample == PU_RS_UP ? a->H * a->W * 4 : (a->resample == PU_RS_DOWN ? a->H * a->W / 4 : a->H * a->W);
-    if (a->dtype == PU_BF16 && a->resample == PU_RS_NONE && gs_enabled()) {
-        const int rb[2] = {a->C0 * 2, a->C1 * 2};
-        GsPlan pl = gs_make_plan(C, rb, 2, 4);
-        const int rows = rows_per_block(OHW, a->N, pl.TR * 4, 2);
-        const int smem = gs_smem_bytes(0, pl.stages, pl.stage_bytes);
-        PU_SMEM_ATTR(gn_apply_tma_kernel, 100 * 1024);
-        PU_REQUIRE(smem <= 100 * 1024, "pu_gn_apply: tile plan needs %d bytes of shared memory", smem);
-        dim3 grid(cdiv(OHW, rows), a->N);
-        gn_apply_tma_kernel<<<grid, GS_THREADS, smem, st>>>(*a, rows, pl);
-        return check_launch("gn_apply_tma");
-    }
     const int PL = GN_THREADS / (C / 8);
     const int rows = rows_per_block(OHW, a->N, PL * 8);
     dim3 grid(cdiv(OHW, rows), a->N);
@@ -1273,7 +1198,7 @@ int pu_gn_bwd(const PuGnBwdArgs* a, void* stream) {
     const bool streamed = f.dtype == PU_BF16 && f.resample == PU_RS_NONE && (!a->dres || a->dres_resample == PU_RS_NONE) &&
                           gs_enabled();
     if (streamed) {
-        // bulk-copy staged kernels (see gn_apply_tma_kernel): same math, shared-memory ring fed by a producer warp
+        // bulk-copy staged kernels (see gn_bwd_reduce_tma_kernel): same math, shared-memory ring fed by a producer warp
         if (!a->du_ready) {
             PU_CUDA(cudaMemsetAsync(a->sums, 0, sizeof(double) * 2 * f.N * C, st));
             const int rb[3] = {f.C0 * 2, C * 2, f.C1 * 2};

@@ -381,7 +381,7 @@ class UNetEngine:
         cs = self._bias_buf(grads, blk.conv0.bias, Cout, dy.device)
         da, _ = ops.gn_bwd(rec['a'], rec['st1'], blk.norm1.weight, blk.norm1.bias, dh1, dg, db, ada=blk.affine.bias,
                            dada=dada, silu=True, dropout_p=rec['p'], seed=rec['seed'], eps=blk.norm1.eps, colsum0=cs,
-                           sums=sums, du_ready=sums is not None)
+                           sums=sums, du_ready=sums is not None, keep_mask=rec.get('mask1'))
         grads[id(blk.norm1.weight)] = dg
         grads[id(blk.norm1.bias)] = db
         grads[id(blk.affine.bias)] = dada

@@ -237,7 +237,7 @@ def gn_apply(src0, stats, gamma, beta, src1=None, ada=None, silu=True, resample=
 def gn_bwd(src0, stats, gamma, beta, dy, dgamma, dbeta, src1=None, ada=None, dada=None, silu=True,
            resample=L.RS_NONE, dropout_p=0.0, seed=0, eps=1e-5, dres=None, dres_resample=L.RS_NONE,
            dx0=None, dx1=None, acc0=False, acc1=False, acc_params=False, colsum0=None, colsum1=None, sums=None,
-           du_ready=False):
+           du_ready=False, keep_mask=None):
     """Returns (dx0, dx1).  dgamma/dbeta/dada are written (or accumulated into when acc_params).
     colsum0 / colsum1 (optional fp32 [C0] / [C1]) receive the per-channel sums of the final dx0 / dx1."""
     N, H, W, C0 = _nhwc(src0)
@@ -251,7 +251,7 @@ def gn_bwd(src0, stats, gamma, beta, dy, dgamma, dbeta, src1=None, ada=None, dad
     if sums is None:
         assert not du_ready
         sums = torch.empty((N, C0 + C1, 2), dtype=torch.float64, device=src0.device)
-    f = _gn_args(src0, src1, stats, gamma, beta, ada, silu, resample, dropout_p, seed, None, eps)
+    f = _gn_args(src0, src1, stats, gamma, beta, ada, silu, resample, dropout_p, seed, None, eps, keep_mask)
     a = L.PuGnBwdArgs(f, ptr(dy), ptr(dres), dres_resample, ptr(sums), ptr(dx0), ptr(dx1), int(acc0), int(acc1),
                       ptr(dgamma), ptr(dbeta), ptr(dada), int(acc_params), ptr(colsum0), ptr(colsum1), int(du_ready))
     check(lib().pu_gn_bwd(C.byref(a), stream_ptr()), 'gn_bwd')
