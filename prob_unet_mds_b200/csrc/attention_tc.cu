@@ -852,6 +852,307 @@ attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// backward kernel, transposed scores (round 2).  ncu on attn_bwd_tc2_kernel (profiles/r2_ncu_attention.md): the eight
+// softmax warps spend 31 % of their time in MIO throttle on the STS.128 of P and dS, 19 % waiting for MUFU results
+// behind the same queue, and the tensor core pulls 224 KB of operands per (q tile, key tile) out of shared memory.
+// Here the CTA computes the TRANSPOSED tiles
+//     S^T = K_j Q_i^T ,  dP^T = V_j dO_i^T            (lanes = keys, columns = queries; two 64-query halves)
+// so that P^T and dS^T are born in the layout the dV / dK accumulations want as their A operand:
+//     dV += P^T dO_i ,  dK += dS^T Q_i                 A straight from TENSOR MEMORY (bf16 pairs written over the first
+//                                                     half of the S^T / dP^T columns each warp has just read)
+//     dQ_i = dS K_j                                    A = dS^T from shared memory, read as an MN-major operand
+// Only dS^T goes through shared memory (4 instead of 8 STS.128 per thread and unit) and the tensor core reads 144 KB
+// per tile pair.  lse_i / delta_i are per-COLUMN constants now: the TMA producer brings the tile's 2 x 512 bytes along
+// with Q_i / dO_i and the softmax threads read them with broadcast LDS.128.  The 1/sqrt(d) of dS is applied once to the
+// dQ partial in the drain warps and to dK at the end (both are linear in dS) instead of per element.
+// Pipeline, barriers and TMEM map follow attn_bwd_tc2_kernel: S^T 0-127 | dP^T 128-255 | dV 256-319 | dK 320-383 |
+// dQ[0] 384-447 | dQ[1] 448-511;  P^T half h, query block w (32 queries) sits in S^T columns [64h + 32w, +16),
+// dS^T in the same columns of dP^T.
+// ------------------------------------------------------------------------------------------------
+constexpr int AB3_LD_BYTES = 2 * AT_TQ * 4;                     // lse_i + delta_i of one q tile
+constexpr int AB3_SMEM = 2 * AT_TILE /*K,V*/ + 2 * 2 * AT_TILE /*Q,dO x2 stages*/ + 2 * 2 * AT_TILE /*dS^T x2*/ +
+                         2 * AB3_LD_BYTES + 1024 + 256;
+
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(AB2_THREADS, 1)
+attn_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                    const AttnBwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sK = smem;
+    uint8_t* sV = sK + AT_TILE;
+    uint8_t* sQD = sV + AT_TILE;                           // stage s: Q at +s*2*TILE, dO at +s*2*TILE + TILE
+    uint8_t* sDS = sQD + 2 * 2 * AT_TILE;                  // buffer b at +b*2*TILE: query half h at +h*TILE, [128 keys][128 B]
+    float* sLD = reinterpret_cast<float*>(sDS + 2 * 2 * AT_TILE);   // stage s: lse[128] then delta[128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sLD) + 2 * AB3_LD_BYTES);
+    uint64_t* kv_full = bars;
+    uint64_t* qd_full = bars + 1;                          // [2]
+    uint64_t* qd_empty = qd_full + 2;                      // [2]  (count 2: the MMA commit and the softmax warps' release of lse/delta)
+    uint64_t* sdp_full = qd_empty + 2;                     // [2] per query half
+    uint64_t* pds_full = sdp_full + 2;                     // [2] per query half
+    uint64_t* ds_free = pds_full + 2;                      // [2] per dS^T buffer
+    uint64_t* dq_full = ds_free + 2;                       // [2] per dQ accumulator
+    uint64_t* dq_empty = dq_full + 2;                      // [2]
+    uint64_t* fin = dq_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fin + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nh = blockIdx.y, n = nh / p.heads, h = nh % p.heads;
+    const int k0 = blockIdx.x * AT_TK;
+    const int nq = p.T / AT_TQ;
+    const int row_base = n * p.T;
+    const int colQ = h * AT_D, colK = p.C + h * AT_D, colV = 2 * p.C + h * AT_D;
+    const float* lse_g = p.lse + ((long long)n * p.heads + h) * p.T;
+    const float* delta_g = p.delta + ((long long)n * p.heads + h) * p.T;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmQKV);
+        prefetch_tmap(&tmDO);
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(smem_u32(kv_full), 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&qd_full[s]), 1);
+            mbar_init(smem_u32(&qd_empty[s]), 1 + 8);  // tcgen05.commit (Q / dO consumed) + 8 softmax warps (lse / delta consumed)
+            mbar_init(smem_u32(&sdp_full[s]), 1);
+            mbar_init(smem_u32(&pds_full[s]), 8);      // one arrive per softmax warp
+            mbar_init(smem_u32(&ds_free[s]), 1);
+            mbar_init(smem_u32(&dq_full[s]), 1);
+            mbar_init(smem_u32(&dq_empty[s]), 4);      // one arrive per drain warp
+        }
+        mbar_init(smem_u32(fin), 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(smem_u32(tmem_slot), 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320,
+                   tDQ = tmem_base + 384;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(smem_u32(kv_full), 2 * AT_TILE);
+            tma_load_2d(smem_u32(sK), &tmQKV, smem_u32(kv_full), colK, row_base + k0);
+            tma_load_2d(smem_u32(sV), &tmQKV, smem_u32(kv_full), colV, row_base + k0);
+            for (int i = 0; i < nq; ++i) {
+                const int stage = i & 1;
+                mbar_wait(smem_u32(&qd_empty[stage]), ((i >> 1) & 1) ^ 1);
+                const uint32_t fb = smem_u32(&qd_full[stage]);
+                mbar_expect_tx(fb, 2 * AT_TILE + AB3_LD_BYTES);
+                const int qi = (i + (int)blockIdx.x) % nq;     // rotated start: see attn_bwd_tc2_kernel
+                tma_load_2d(smem_u32(sQD + stage * 2 * AT_TILE), &tmQKV, fb, colQ, row_base + qi * AT_TQ);
+                tma_load_2d(smem_u32(sQD + stage * 2 * AT_TILE + AT_TILE), &tmDO, fb, colQ, row_base + qi * AT_TQ);
+                bulk_load_1d(smem_u32(sLD + stage * 2 * AT_TQ), lse_g + qi * AT_TQ, AT_TQ * 4, fb);
+                bulk_load_1d(smem_u32(sLD + stage * 2 * AT_TQ + AT_TQ), delta_g + qi * AT_TQ, AT_TQ * 4, fb);
+            }
+        }
+    } else if (warp == 1) {
+        // whole warp, warp-uniform control flow; the mma helpers elect one lane internally
+        constexpr uint32_t IDESC_H = idesc_bf16_f32(128, 64, 0, 0);      // S^T, dP^T halves: A = K / V, B = 64 rows of Q / dO
+        constexpr uint32_t IDESC_A = idesc_bf16_f32(128, 64, 0, 1);      // dV, dK: A in TMEM, B = dO / Q rows (MN-major)
+        constexpr uint32_t IDESC_Q = idesc_bf16_f32(128, 64, 1, 1);      // dQ: A = dS^T (MN-major), B = K (MN-major)
+        const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+        mbar_wait(smem_u32(kv_full), 0);
+        auto issue_sdp = [&](int stage, int half) {
+            const uint32_t qh = smem_u32(sQD + stage * 2 * AT_TILE) + half * (AT_TILE / 2);   // rows [64 half, +64) of Q_i
+            const uint32_t doh = qh + AT_TILE;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                mma_f16_ss(tS + half * 64, smem_desc_sw128(k_addr + k * 32, 16, 1024), smem_desc_sw128(qh + k * 32, 16, 1024),
+                           IDESC_H, k ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                mma_f16_ss(tDP + half * 64, smem_desc_sw128(v_addr + k * 32, 16, 1024),
+                           smem_desc_sw128(doh + k * 32, 16, 1024), IDESC_H, k ? 1u : 0u);
+            mma_commit(smem_u32(&sdp_full[half]));
+        };
+        // dV += P^T_half dO_half, dK += dS^T_half Q_half: K = the half's 64 queries, 16 per step; the A operand of step k
+        // (queries [16k, +16) of the half) is the 8 packed columns at [64 half + 32 (k >> 1) + 8 (k & 1)]
+        auto issue_dvdk = [&](int stage, int half, bool first) {
+            const uint32_t q_addr = smem_u32(sQD + stage * 2 * AT_TILE);
+            const uint32_t do_addr = q_addr + AT_TILE;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t col = half * 64 + (k >> 1) * 32 + (k & 1) * 8;
+                mma_f16_ts(tDV, tS + col, smem_desc_sw128(do_addr + (half * 4 + k) * 2048, AT_TILE, 1024), IDESC_A,
+                           (first && k == 0) ? 0u : 1u);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t col = half * 64 + (k >> 1) * 32 + (k & 1) * 8;
+                mma_f16_ts(tDK, tDP + col, smem_desc_sw128(q_addr + (half * 4 + k) * 2048, AT_TILE, 1024), IDESC_A,
+                           (first && k == 0) ? 0u : 1u);
+            }
+        };
+        mbar_wait(smem_u32(&qd_full[0]), 0);
+        tc_fence_after();
+        issue_sdp(0, 0);
+        issue_sdp(0, 1);
+        for (int i = 0; i < nq; ++i) {
+            const int stage = i & 1;
+            const uint32_t ds_addr = smem_u32(sDS + stage * 2 * AT_TILE);
+            const uint32_t tDQb = tDQ + (uint32_t)(i & 1) * 64;
+            // ---- query half 0 ----
+            mbar_wait(smem_u32(&pds_full[0]), i & 1);
+            tc_fence_after();
+            issue_dvdk(stage, 0, i == 0);
+            if (i + 1 < nq) {
+                mbar_wait(smem_u32(&qd_full[stage ^ 1]), ((i + 1) >> 1) & 1);
+                tc_fence_after();
+                issue_sdp(stage ^ 1, 0);
+            }
+            // ---- query half 1 ----
+            mbar_wait(smem_u32(&pds_full[1]), i & 1);
+            if (i >= 2) mbar_wait(smem_u32(&dq_empty[i & 1]), ((i >> 1) - 1) & 1);   // tile i-2 drained from this accumulator
+            tc_fence_after();
+            issue_dvdk(stage, 1, false);
+            // dQ_i [128 q x 64] = dS [q x k] K [k x d]: A = dS^T buffer read MN-major (M = queries contiguous, two 64-query
+            // blocks AT_TILE apart), 16 keys (= 16 rows of 128 B) per step; B = K rows (MN-major)
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                mma_f16_ss(tDQb, smem_desc_sw128(ds_addr + k * 2048, AT_TILE, 1024),
+                           smem_desc_sw128(k_addr + k * 2048, AT_TILE, 1024), IDESC_Q, k ? 1u : 0u);
+            mma_commit(smem_u32(&dq_full[i & 1]));
+            mma_commit(smem_u32(&qd_empty[stage]));
+            mma_commit(smem_u32(&ds_free[stage]));
+            if (i + 1 < nq) issue_sdp(stage ^ 1, 1);
+        }
+        mma_commit(smem_u32(fin));
+    } else if (warp >= 12) {
+        // dQ drain warpgroup (as in attn_bwd_tc2_kernel), with the 1/sqrt(d) of dS applied here
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        for (int i = 0; i < nq; ++i) {
+            const int b = i & 1;
+            const int qi = (i + (int)blockIdx.x) % nq;
+            mbar_wait(smem_u32(&dq_full[b]), (i >> 1) & 1);
+            tc_fence_after();
+            uint32_t v0[32], v1[32];
+            tmem_ld32(tDQ + b * 64 + lane_off, v0);
+            tmem_ld32(tDQ + b * 64 + lane_off + 32, v1);
+            tc_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&dq_empty[b]));
+            float* dst = p.dq_acc + ((long long)row_base + qi * AT_TQ + r) * p.C + h * AT_D;
+#pragma unroll
+            for (int e = 0; e < 32; e += 4)
+                red_add_v4(dst + e, 0.125f * __uint_as_float(v0[e]), 0.125f * __uint_as_float(v0[e + 1]),
+                           0.125f * __uint_as_float(v0[e + 2]), 0.125f * __uint_as_float(v0[e + 3]));
+#pragma unroll
+            for (int e = 0; e < 32; e += 4)
+                red_add_v4(dst + 32 + e, 0.125f * __uint_as_float(v1[e]), 0.125f * __uint_as_float(v1[e + 1]),
+                           0.125f * __uint_as_float(v1[e + 2]), 0.125f * __uint_as_float(v1[e + 3]));
+        }
+    } else if (warp >= 4) {
+        // eight softmax warps: warp quadrant q owns KEY rows (= TMEM lanes) [32q, 32q+32); within a 64-query half warpgroup
+        // wg handles the query columns [32wg, 32wg+32)
+        const int q = warp & 3;
+        const int wg = (warp - 4) >> 2;
+        const int r = q * 32 + lane;                       // key row of this thread
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        const float sc = 0.125f * 1.4426950408889634f;
+        auto unit = [&](int i, int half) {
+            const int b = i & 1;
+            const int c = half * 64 + wg * 32;             // first query column of this thread's chunk
+            if (half == 0) mbar_wait(smem_u32(&qd_full[b]), (i >> 1) & 1);   // lse / delta of tile i are in shared memory
+            mbar_wait(smem_u32(&sdp_full[half]), i & 1);
+            tc_fence_after();
+            uint32_t sv[32], dv[32];
+            tmem_ld32(tS + lane_off + c, sv);
+            tmem_ld32(tDP + lane_off + c, dv);
+            // the dQ MMAs of tile i-2 must have finished reading this dS^T buffer
+            if (half == 0) mbar_wait(smem_u32(&ds_free[b]), ((i >> 1) & 1) ^ 1);
+            const float4* l4 = reinterpret_cast<const float4*>(sLD + b * 2 * AT_TQ + c);
+            const float4* d4 = reinterpret_cast<const float4*>(sLD + b * 2 * AT_TQ + AT_TQ + c);
+            tc_wait_ld();
+            uint32_t pk[16], dk[16];
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                const float4 l = l4[g], d = d4[g];         // broadcast reads: every lane of the warp wants the same columns
+                const float lv[4] = {l.x, l.y, l.z, l.w}, dl[4] = {d.x, d.y, d.z, d.w};
+                float pv[4], dsv[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int j = g * 4 + e;
+                    pv[e] = ex2_approx(fmaf(__uint_as_float(sv[j]), sc, -1.4426950408889634f * lv[e]));
+                    dsv[e] = pv[e] * (__uint_as_float(dv[j]) - dl[e]);       // unscaled: 1/sqrt(d) is applied to dQ and dK
+                }
+                const __nv_bfloat162 p0 = __floats2bfloat162_rn(pv[0], pv[1]), p1 = __floats2bfloat162_rn(pv[2], pv[3]);
+                const __nv_bfloat162 s0 = __floats2bfloat162_rn(dsv[0], dsv[1]), s1 = __floats2bfloat162_rn(dsv[2], dsv[3]);
+                pk[2 * g] = *reinterpret_cast<const uint32_t*>(&p0);
+                pk[2 * g + 1] = *reinterpret_cast<const uint32_t*>(&p1);
+                dk[2 * g] = *reinterpret_cast<const uint32_t*>(&s0);
+                dk[2 * g + 1] = *reinterpret_cast<const uint32_t*>(&s1);
+            }
+            // P^T / dS^T as TMEM A operands, over the first 16 of the 32 columns this warp has just read
+            tmem_st16(tS + lane_off + c, pk);
+            tmem_st16(tDP + lane_off + c, dk);
+            // dS^T row `r` (this key), queries [c, c+32) -> 64 bytes = chunks [4 wg, +4) of the half's SW128 row
+            uint8_t* db = sDS + b * 2 * AT_TILE + half * AT_TILE + r * 128;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int off = ((wg * 4 + g) ^ (r & 7)) << 4;
+                *reinterpret_cast<uint4*>(db + off) = make_uint4(dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
+            }
+            tc_wait_st();
+            tc_fence_before();
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(smem_u32(&pds_full[half]));
+                if (half == 1) mbar_arrive(smem_u32(&qd_empty[b]));   // lse / delta of this stage no longer needed
+            }
+        };
+        for (int i = 0; i < nq; ++i) {
+            unit(i, 0);
+            unit(i, 1);
+        }
+        // final dV / dK: wait until every MMA of this CTA has completed
+        mbar_wait(smem_u32(fin), 0);
+        tc_fence_after();
+        __nv_bfloat16* kp = p.dqkv + ((long long)row_base + k0 + r) * 3 * p.C + colK;
+        __nv_bfloat16* vp = p.dqkv + ((long long)row_base + k0 + r) * 3 * p.C + colV;
+        {
+            const int c = wg * 32;
+            uint32_t a[32], b[32];
+            tmem_ld32(tDK + lane_off + c, a);
+            tmem_ld32(tDV + lane_off + c, b);
+            tc_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 32; e += 16) {
+                float ka[16], va[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    ka[u] = 0.125f * __uint_as_float(a[e + u]);
+                    va[u] = __uint_as_float(b[e + u]);
+                }
+                st16(kp + c + e, ka);
+                st16(vp + c + e, va);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 // dqkv[row][0:C] = bf16(dq_acc[row][:])
 __global__ void attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, long long rows,
                                        int C) {
@@ -882,8 +1183,14 @@ int attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const 
     p.lse = lse; p.delta = delta; p.dq_acc = dq_acc;
     p.dqkv = (__nv_bfloat16*)dqkv;
     dim3 grid(T / AT_TK, N * heads);
-    PU_SMEM_ATTR(attn_bwd_tc2_kernel, AB2_SMEM);
-    attn_bwd_tc2_kernel<<<grid, AB2_THREADS, AB2_SMEM, st>>>(tm, tmdo, p);
+    static const int variant = getenv("PU_ATTN_BWD") ? atoi(getenv("PU_ATTN_BWD")) : 3;   // 2: the round-1 layout (A/B runs)
+    if (variant == 2) {
+        PU_SMEM_ATTR(attn_bwd_tc2_kernel, AB2_SMEM);
+        attn_bwd_tc2_kernel<<<grid, AB2_THREADS, AB2_SMEM, st>>>(tm, tmdo, p);
+    } else {
+        PU_SMEM_ATTR(attn_bwd_tc3_kernel, AB3_SMEM);
+        attn_bwd_tc3_kernel<<<grid, AB2_THREADS, AB3_SMEM, st>>>(tm, tmdo, p);
+    }
     rc = check_launch("attn_bwd_tc");
     if (rc) return rc;
     long long total = (long long)N * T * (C / 8);
