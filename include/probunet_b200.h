@@ -49,8 +49,9 @@ int pu_copy(void* dst, const void* src, long long bytes, void* stream);
  * layout of torch.cat([x, target], 1) (prob_unet.py:58) and the fp32->bf16 cast of the model inputs.            */
 int pu_nchw_to_nhwc(const float* src, void* dst, int N, int C, int H, int W, int Cdst, int c_off, int dst_dtype,
                     void* stream);
-/* NHWC (dtype) -> fp32 NCHW; the model output handed back to the caller (prob_unet.py:195-196). */
-int pu_nhwc_to_nchw(const void* src, float* dst, int N, int C, int H, int W, int src_dtype, void* stream);
+/* NHWC (dtype) -> fp32 NCHW; the model output handed back to the caller (prob_unet.py:195-196).  The source has Csrc >= C
+ * channels per pixel and its first C are taken (a 3-channel output head computed in a zero-padded 64-channel tile). */
+int pu_nhwc_to_nchw(const void* src, float* dst, int N, int C, int H, int W, int Csrc, int src_dtype, void* stream);
 /* fp32 NCHW grad <- NHWC fp32 etc. are not needed: the reference never asks for input gradients. */
 
 /* OIHW fp32 master weight -> packed weight in `dtype`.

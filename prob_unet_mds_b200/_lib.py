@@ -65,7 +65,7 @@ _SIGNATURES = {
     'pu_zero': (c_int, [c_void_p, c_ll, c_void_p]),
     'pu_copy': (c_int, [c_void_p, c_void_p, c_ll, c_void_p]),
     'pu_nchw_to_nhwc': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    'pu_nhwc_to_nchw': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'pu_nhwc_to_nchw': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'pu_pack_conv_weight': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_int, c_void_p]),
     'pu_pack_conv_weights_multi': (c_int, [c_void_p, c_int, c_int, c_void_p]),
     'pu_unpack_conv_wgrad': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_int, c_void_p]),

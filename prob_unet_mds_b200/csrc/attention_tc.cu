@@ -48,7 +48,7 @@ __device__ __forceinline__ float ex2_poly(float x) {
 }
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
-    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));      // not volatile: a pure function the scheduler may move
     return y;
 }
 
@@ -593,6 +593,9 @@ constexpr int AB2_SMEM = 2 * AT_TILE /*K,V*/ + 2 * 2 * AT_TILE /*Q,dO x2 stages*
 
 constexpr int AB2_THREADS = 512;
 
+// POLY: every POLY-th exponential of a thread is evaluated on the FMA pipe (ex2_poly) instead of MUFU.EX2; 0 = none.
+// MUFU instructions share the MIO queue with the STS.128 of P / dS, which is where the softmax warps stall.
+template <int POLY>
 __global__ void __launch_bounds__(AB2_THREADS, 1)
 attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                     const AttnBwdParams p) {
@@ -773,7 +776,7 @@ attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         const float sc = 0.125f * 1.4426950408889634f;
         const float* lse = p.lse + ((long long)n * p.heads + h) * p.T;
         const float* delta = p.delta + ((long long)n * p.heads + h) * p.T;
-        float l2 = 0.f, dl = 0.f;
+        float l2 = 0.f, dl = 0.f;                 // lse * log2(e) and delta / sqrt(d) of this thread's query row
         auto unit = [&](int i, int half) {
             const int b = i & 1;
             mbar_wait(smem_u32(&sdp_full[half]), i & 1);
@@ -796,10 +799,11 @@ attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int i0 = g * 8 + 2 * e;
-                    const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i0]), sc, -l2));
-                    const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i0 + 1]), sc, -l2));
-                    const float d0 = p0 * (__uint_as_float(dv[i0]) - dl) * 0.125f;
-                    const float d1 = p1 * (__uint_as_float(dv[i0 + 1]) - dl) * 0.125f;
+                    const float x0 = fmaf(__uint_as_float(sv[i0]), sc, -l2), x1 = fmaf(__uint_as_float(sv[i0 + 1]), sc, -l2);
+                    const float p0 = (POLY > 0 && (i0 % POLY) == POLY - 1) ? ex2_poly(x0) : ex2_approx(x0);
+                    const float p1 = (POLY > 0 && ((i0 + 1) % POLY) == POLY - 1) ? ex2_poly(x1) : ex2_approx(x1);
+                    const float d0 = p0 * fmaf(__uint_as_float(dv[i0]), 0.125f, -dl);
+                    const float d1 = p1 * fmaf(__uint_as_float(dv[i0 + 1]), 0.125f, -dl);
                     hp[e] = __floats2bfloat162_rn(p0, p1);
                     hd[e] = __floats2bfloat162_rn(d0, d1);
                 }
@@ -815,7 +819,7 @@ attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         for (int i = 0; i < nq; ++i) {
             const int qi = (i + (int)blockIdx.x) % nq;     // same rotation as the TMA producer
             l2 = lse[qi * AT_TQ + r] * 1.4426950408889634f;
-            dl = delta[qi * AT_TQ + r];
+            dl = 0.125f * delta[qi * AT_TQ + r];
             unit(i, 0);
             unit(i, 1);
         }
@@ -1183,10 +1187,19 @@ int attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const 
     p.lse = lse; p.delta = delta; p.dq_acc = dq_acc;
     p.dqkv = (__nv_bfloat16*)dqkv;
     dim3 grid(T / AT_TK, N * heads);
-    static const int variant = getenv("PU_ATTN_BWD") ? atoi(getenv("PU_ATTN_BWD")) : 3;   // 2: the round-1 layout (A/B runs)
-    if (variant == 2) {
-        PU_SMEM_ATTR(attn_bwd_tc2_kernel, AB2_SMEM);
-        attn_bwd_tc2_kernel<<<grid, AB2_THREADS, AB2_SMEM, st>>>(tm, tmdo, p);
+    // PU_ATTN_BWD (A/B runs): 3 = transposed scores (attn_bwd_tc3_kernel, measured 6 % slower: 56 instead of 42 MIO
+    // instructions per thread and half-tile), 20 / 22 / 24 = attn_bwd_tc2_kernel with no / every 2nd / every 4th
+    // exponential on the FMA pipe
+    static const int variant = getenv("PU_ATTN_BWD") ? atoi(getenv("PU_ATTN_BWD")) : 22;
+    if (variant == 20) {
+        PU_SMEM_ATTR(attn_bwd_tc2_kernel<0>, AB2_SMEM);
+        attn_bwd_tc2_kernel<0><<<grid, AB2_THREADS, AB2_SMEM, st>>>(tm, tmdo, p);
+    } else if (variant == 22) {
+        PU_SMEM_ATTR(attn_bwd_tc2_kernel<2>, AB2_SMEM);
+        attn_bwd_tc2_kernel<2><<<grid, AB2_THREADS, AB2_SMEM, st>>>(tm, tmdo, p);
+    } else if (variant == 24) {
+        PU_SMEM_ATTR(attn_bwd_tc2_kernel<4>, AB2_SMEM);
+        attn_bwd_tc2_kernel<4><<<grid, AB2_THREADS, AB2_SMEM, st>>>(tm, tmdo, p);
     } else {
         PU_SMEM_ATTR(attn_bwd_tc3_kernel, AB3_SMEM);
         attn_bwd_tc3_kernel<<<grid, AB2_THREADS, AB3_SMEM, st>>>(tm, tmdo, p);

@@ -18,14 +18,14 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict
 }
 
 template <typename T>
-__global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int N, int C, int HW) {
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int N, int C, int HW, int Csrc) {
     long long total = (long long)N * HW * C;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         int hw = (int)(i % HW);
         long long t = i / HW;
         int c = (int)(t % C);
         int n = (int)(t / C);
-        dst[i] = ldf(src + ((long long)n * HW + hw) * C + c);
+        dst[i] = ldf(src + ((long long)n * HW + hw) * Csrc + c);
     }
 }
 
@@ -223,15 +223,15 @@ int pu_nchw_to_nhwc(const float* src, void* dst, int N, int C, int H, int W, int
     return pu::check_launch("nchw_to_nhwc");
 }
 
-int pu_nhwc_to_nchw(const void* src, float* dst, int N, int C, int H, int W, int src_dtype, void* stream) {
-    PU_REQUIRE(src && dst && N > 0 && C > 0 && H > 0 && W > 0, "pu_nhwc_to_nchw: bad arguments");
+int pu_nhwc_to_nchw(const void* src, float* dst, int N, int C, int H, int W, int Csrc, int src_dtype, void* stream) {
+    PU_REQUIRE(src && dst && N > 0 && C > 0 && H > 0 && W > 0 && Csrc >= C, "pu_nhwc_to_nchw: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     long long total = (long long)N * C * H * W;
     if (src_dtype == PU_F32)
-        pu::nhwc_to_nchw_kernel<float><<<pu::grid_for(total), 256, 0, st>>>((const float*)src, dst, N, C, H * W);
+        pu::nhwc_to_nchw_kernel<float><<<pu::grid_for(total), 256, 0, st>>>((const float*)src, dst, N, C, H * W, Csrc);
     else
         pu::nhwc_to_nchw_kernel<__nv_bfloat16><<<pu::grid_for(total), 256, 0, st>>>((const __nv_bfloat16*)src, dst, N,
-                                                                                  C, H * W);
+                                                                                  C, H * W, Csrc);
     return pu::check_launch("nhwc_to_nchw");
 }
 

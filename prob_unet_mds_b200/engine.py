@@ -123,6 +123,29 @@ class UNetEngine:
     def w_dgrad(self, p, perm=None):
         return self.cache.get_weight((id(p), 'd', self.dtype), p, self.dtype, 1, perm=perm)
 
+    def out_pad(self):
+        """Channel count the output head is computed with: a head with few output channels (the deterministic U-Net's
+        64 -> 3 conv at full resolution, baseline/deterministic_unet.py:296) would run forward, data gradient and weight
+        gradient on the CUDA-core kernels (18 of 70 ms per step at 256x256, batch 32); zero-padded to 64 output channels it
+        runs on the tcgen05 kernels and the first `out_channels` channels are what leaves the engine."""
+        Co = self.unet.out_conv.out_channels
+        return 64 if (self.dtype == torch.bfloat16 and Co < 64) else Co
+
+    def _w_out_padded(self, p, mode):
+        def make():
+            Co, Ci, k, _ = p.shape
+            wp = ops.zeros((64, Ci, k, k), torch.float32, p.device)
+            ops.clone(p.detach().reshape(-1), out=wp.reshape(-1)[:p.numel()])      # OIHW: the first Co rows are contiguous
+            return ops.pack_weight(wp, mode, self.dtype)
+        return self.cache.get((id(p), 'opad', mode, self.dtype), p, make)
+
+    def _b_out_padded(self, p):
+        def make():
+            bp = ops.zeros((64,), torch.float32, p.device)
+            ops.clone(p.detach(), out=bp[:p.numel()])
+            return bp
+        return self.cache.get((id(p), 'obpad'), p, make)
+
     def qkv_perm(self, C, heads, device):
         """my channel (j, head, d) -> reference channel head*192 + d*3 + j  (networks.py:180 reshape/unbind)."""
         key = (C, heads, str(device))
@@ -178,7 +201,11 @@ class UNetEngine:
                 tape.append(rec)
         st = self._stats(x)
         h = ops.gn_apply(x, st, u.out_norm.weight, u.out_norm.bias, silu=True, eps=u.out_norm.eps)
-        feat = ops.conv2d(h, self.w_fwd(u.out_conv.weight), u.out_conv.out_channels, 3, bias=u.out_conv.bias)
+        if self.out_pad() != u.out_conv.out_channels:
+            feat = ops.conv2d(h, self._w_out_padded(u.out_conv.weight, 0), self.out_pad(), 3,
+                              bias=self._b_out_padded(u.out_conv.bias))
+        else:
+            feat = ops.conv2d(h, self.w_fwd(u.out_conv.weight), u.out_conv.out_channels, 3, bias=u.out_conv.bias)
         if save:
             tape.append(dict(kind='out', x=x, st=st, h=h, out=feat, bias_x=self._prod.get(id(x))))
         self._q = {}
@@ -315,9 +342,14 @@ class UNetEngine:
         rec = tape[-1]
         # order everywhere below: data gradient first, then the weight gradient (side stream, starts once the dgrad
         # has finished) so that it runs under the GroupNorm-backward kernels that follow on the main stream
-        grads[id(u.out_conv.bias)] = ops.bias_grad(dfeat, db=grads.alloc(u.out_conv.bias))
-        dh, sums = self._dgrad_gn(dfeat, self.w_dgrad(u.out_conv.weight), rec['h'].shape[3], 3, rec['x'], rec['st'],
-                                  u.out_norm)
+        Co = u.out_conv.out_channels
+        if dfeat.shape[3] != Co:            # padded head (out_pad): dfeat carries zero channels beyond Co
+            grads[id(u.out_conv.bias)] = ops.clone(ops.bias_grad(dfeat)[:Co].contiguous(), out=grads.alloc(u.out_conv.bias))
+            w_d = self._w_out_padded(u.out_conv.weight, 1)
+        else:
+            grads[id(u.out_conv.bias)] = ops.bias_grad(dfeat, db=grads.alloc(u.out_conv.bias))
+            w_d = self.w_dgrad(u.out_conv.weight)
+        dh, sums = self._dgrad_gn(dfeat, w_d, rec['h'].shape[3], 3, rec['x'], rec['st'], u.out_norm)
         self._wgrad(grads, u.out_conv.weight, rec['h'], dfeat, 3)
         dg = grads.alloc(u.out_norm.weight)
         db = grads.alloc(u.out_norm.bias)
@@ -467,13 +499,13 @@ class _UNetFunction(torch.autograd.Function):
         eng._step += 1
         feat, tape = eng.forward(xs, unet.training, True, seed_base=_seed_base(eng._step))
         ctx.tape = tape
-        return ops.nhwc_to_nchw(feat)
+        return ops.nhwc_to_nchw(feat, C=unet.out_conv.out_channels)
 
     @staticmethod
     def backward(ctx, dout):
         unet = ctx.unet
         eng = unet.engine()
-        dfeat = ops.nchw_to_nhwc(dout.contiguous().float(), eng.dtype)
+        dfeat = ops.nchw_to_nhwc(dout.contiguous().float(), eng.dtype, Cdst=eng.out_pad())
         grads = new_grad_sink(unet)
         eng.backward(ctx.tape, dfeat, grads)
         grads.finish()
@@ -499,7 +531,7 @@ def unet_apply(unet, x):
     xs = input_nhwc(x, eng.dtype)
     eng._step += 1
     feat, _ = eng.forward(xs, unet.training, False, seed_base=_seed_base(eng._step))
-    return ops.nhwc_to_nchw(feat)
+    return ops.nhwc_to_nchw(feat, C=unet.out_conv.out_channels)
 
 
 # ======================================================================================================================

@@ -48,10 +48,12 @@ def nchw_to_nhwc(x, dtype, out=None, c_off=0, Cdst=None):
     return out
 
 
-def nhwc_to_nchw(x):
-    N, H, W, Cc = _nhwc(x)
+def nhwc_to_nchw(x, C=None):
+    """C: take only the first C channels of x (default: all)."""
+    N, H, W, Csrc = _nhwc(x)
+    Cc = C or Csrc
     out = torch.empty((N, Cc, H, W), dtype=torch.float32, device=x.device)
-    check(lib().pu_nhwc_to_nchw(ptr(x), ptr(out), N, Cc, H, W, dtype_code(x.dtype), stream_ptr()), 'nhwc_to_nchw')
+    check(lib().pu_nhwc_to_nchw(ptr(x), ptr(out), N, Cc, H, W, Csrc, dtype_code(x.dtype), stream_ptr()), 'nhwc_to_nchw')
     return out
 
 
@@ -105,8 +107,10 @@ def pack_weights_multi(table, n_items, total_tiles):
 
 
 def unpack_wgrad(dw_packed, grad, perm=None, Ci=None, dst_co_stride=0, accumulate=False):
-    """dw_packed: fp32 [Co, k, k, Ci_pad]; grad: fp32 OIHW destination."""
-    Co, k, _, Ci_pad = dw_packed.shape
+    """dw_packed: fp32 [Co', k, k, Ci_pad] with Co' >= Co (rows beyond the destination's Co are padding and ignored);
+    grad: fp32 OIHW destination."""
+    _, k, _, Ci_pad = dw_packed.shape
+    Co = min(dw_packed.shape[0], grad.shape[0])
     Ci = Ci if Ci is not None else grad.shape[1]
     check(lib().pu_unpack_conv_wgrad(ptr(dw_packed), ptr(grad), Co, Ci, k, Ci_pad, ptr(perm), dst_co_stride,
                                      int(accumulate), stream_ptr()), 'unpack_conv_wgrad')
