@@ -1187,16 +1187,14 @@ int attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const 
     p.lse = lse; p.delta = delta; p.dq_acc = dq_acc;
     p.dqkv = (__nv_bfloat16*)dqkv;
     dim3 grid(T / AT_TK, N * heads);
-    // PU_ATTN_BWD (A/B runs): 3 = transposed scores (attn_bwd_tc3_kernel, measured 6 % slower: 56 instead of 42 MIO
-    // instructions per thread and half-tile), 20 / 22 / 24 = attn_bwd_tc2_kernel with no / every 2nd / every 4th
-    // exponential on the FMA pipe
-    static const int variant = getenv("PU_ATTN_BWD") ? atoi(getenv("PU_ATTN_BWD")) : 22;
+    // PU_ATTN_BWD (A/B runs; measured at T = 4096, heads = 4, batch 64): default = attn_bwd_tc2_kernel<0>, 4.72 - 4.75 ms;
+    // 24 = every 4th exponential on the FMA pipe, 4.72 ms (every 2nd: 4.85 ms, removed); 3 = transposed scores
+    // (attn_bwd_tc3_kernel), 5.00 ms: half the shared-memory traffic but 56 instead of 42 MIO-queue instructions (MUFU,
+    // LDS, STS, LDTM / STTM) per thread and half-tile, and that queue is what the softmax warps stall on
+    static const int variant = getenv("PU_ATTN_BWD") ? atoi(getenv("PU_ATTN_BWD")) : 20;
     if (variant == 20) {
         PU_SMEM_ATTR(attn_bwd_tc2_kernel<0>, AB2_SMEM);
         attn_bwd_tc2_kernel<0><<<grid, AB2_THREADS, AB2_SMEM, st>>>(tm, tmdo, p);
-    } else if (variant == 22) {
-        PU_SMEM_ATTR(attn_bwd_tc2_kernel<2>, AB2_SMEM);
-        attn_bwd_tc2_kernel<2><<<grid, AB2_THREADS, AB2_SMEM, st>>>(tm, tmdo, p);
     } else if (variant == 24) {
         PU_SMEM_ATTR(attn_bwd_tc2_kernel<4>, AB2_SMEM);
         attn_bwd_tc2_kernel<4><<<grid, AB2_THREADS, AB2_SMEM, st>>>(tm, tmdo, p);

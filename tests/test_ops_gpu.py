@@ -537,6 +537,43 @@ def test_attention_tc(N, T, heads):
     assert eb < 1.5e-2 and max(parts) < 2e-2
 
 
+_ATTN_VARIANT_SNIPPET = r"""
+import sys, torch
+sys.path.insert(0, {root!r})
+from prob_unet_mds_b200 import _lib as L, ops
+g = torch.Generator().manual_seed(0)
+worst = 0.0
+for (N, T, heads) in ((2, 128, 2), (1, 1024, 4), (3, 384, 6)):
+    C = heads * 64
+    qkv = (torch.randn(N, T, 3 * C, generator=g) * 1.5).cuda().bfloat16().float().requires_grad_(True)
+    q, k, v = [t.reshape(N, T, heads, 64).permute(0, 2, 1, 3) for t in qkv.split(C, dim=-1)]
+    ref = (torch.softmax(q @ k.transpose(-1, -2) / 8.0, dim=-1) @ v).permute(0, 2, 1, 3).reshape(N, T, C)
+    dout = torch.randn(N, T, C, generator=g).cuda().bfloat16().float()
+    ref.backward(dout)
+    out, lse = ops.attention_fwd(qkv.detach().bfloat16(), heads, flags=L.CONV_FORCE_TC)
+    dqkv = ops.attention_bwd(qkv.detach().bfloat16(), out, dout.bfloat16(), lse, heads, flags=L.CONV_FORCE_TC)
+    worst = max(worst, ((dqkv.float() - qkv.grad).norm() / qkv.grad.norm()).item())
+print('WORST', worst)
+"""
+
+
+@pytest.mark.parametrize('variant', ['24', '3'])
+def test_attention_bwd_variants(variant):
+    """The attention-backward kernels that are not the default (PU_ATTN_BWD: 24 = every 4th exponential on the FMA pipe,
+    3 = transposed scores with P^T / dS^T as tensor-memory operands) against autograd, one interpreter each (the switch is
+    read once per process)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, '-c', _ATTN_VARIANT_SNIPPET.format(root=root)], capture_output=True, text=True,
+                       env=dict(os.environ, PU_ATTN_BWD=variant), timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    worst = float(r.stdout.strip().split('WORST')[-1])
+    print(f'PU_ATTN_BWD={variant}: worst rel err {worst:.3e}')
+    assert worst < 1.5e-2
+
+
 def test_attention_tc_score_jumps():
     """The forward kernel's softmax uses the running maximum of the *previous* key tiles as the reference of the current
     one and falls back to the exact two-pass scheme when a score exceeds it by more than 2^64.  Build that case: keys in
