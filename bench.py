@@ -310,7 +310,12 @@ def bench_train(ctx, args, model, opt, ddp):
     if sampler:
         sampler.start()
     L._raw_lib().pu_launch_count(1)
+    ncu_range = os.environ.get('PU_NCU_RANGE') == '1'      # scripts/gpu_launch_list.sh: `ncu --profile-from-start off`
+    if ncu_range:                                          # captures exactly the steady-state timed steps
+        torch.cuda.profiler.start()
     out['ms_resident'] = ctx.timed(lambda: step(x_dev, t_dev), args.steps, 0)
+    if ncu_range:
+        torch.cuda.profiler.stop()
     out['launches'] = int(L._raw_lib().pu_launch_count(0))
     out['clocks'] = sampler.stop() if sampler else None
 

@@ -1,5 +1,5 @@
 """Launches every heavy kernel of one ELBO step once (after one warm-up launch each) at the headline shapes
-(batch 64, 128x128 input), for `ncu --set full`.  Order = the order of the rows in profiles/r1_ncu_heavy_kernels.tsv."""
+(batch 64, 128x128 input), for `ncu --set full`.  Order = the order of the rows in profiles/r2_ncu_heavy_kernels.tsv."""
 import os
 import sys
 
@@ -28,7 +28,15 @@ def conv_case(c0, co, hw, k):
     wf, wd = ops.pack_weight(w, 0, dt), ops.pack_weight(w, 1, dt)
     bias = torch.randn(co, device=dev)
     twice(lambda: ops.conv2d(x, wf, co, k, bias=bias, flags=L.CONV_FORCE_TC))      # forward
+    twice(lambda: ops.conv2d(x, wf, co, k, bias=bias, flags=L.CONV_FORCE_TC, want_qstats=True))   # + GroupNorm statistics
     twice(lambda: ops.conv2d(dy, wd, c0, k, flags=L.CONV_FORCE_TC))                # dgrad
+    if k == 3:                                                                     # dgrad + GroupNorm-backward epilogue
+        gam, bet, ada = torch.ones(c0, device=dev), torch.zeros(c0, device=dev), torch.zeros(2 * c0, device=dev)
+        st = ops.gn_stats(x)
+        mask = torch.empty(x.numel() // 8, dtype=torch.uint8, device=dev)
+        ops.gn_apply(x, st, gam, bet, ada=ada, silu=True, dropout_p=0.1, seed=1, keep_mask=mask)
+        d, sums, keep = ops.gn_bwd_epilogue(x, st, gam, bet, ada=ada, silu=True, dropout_p=0.1, seed=1, keep_mask=mask)
+        twice(lambda: ops.conv2d(dy, wd, c0, k, flags=L.CONV_FORCE_TC, gn_bwd=d))
     twice(lambda: ops.conv2d_wgrad(x, dy, k, flags=L.CONV_FORCE_TC))               # wgrad
 
 
