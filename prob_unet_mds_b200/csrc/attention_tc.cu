@@ -46,6 +46,19 @@ __device__ __forceinline__ float ex2_poly(float x) {
     pz = fmaf(pz, f, 1.0f);
     return __int_as_float(__float_as_int(pz) + (__float_as_int(t) << 23));
 }
+// two of them at once with packed fp32 instructions (FFMA2 / FADD2): ~5.5 instead of 8 instructions per exponential
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+    x.x = fmaxf(x.x, -120.f);
+    x.y = fmaxf(x.y, -120.f);
+    const float2 magic = make_float2(12582912.f, 12582912.f);
+    const float2 t = fadd2(x, magic);
+    const float2 f = fadd2(x, fadd2(magic, make_float2(-t.x, -t.y)));          // x - (t - magic)
+    float2 pz = ffma2(f, make_float2(0.0555041f, 0.0555041f), make_float2(0.2402265f, 0.2402265f));
+    pz = ffma2(pz, f, make_float2(0.6931472f, 0.6931472f));
+    pz = ffma2(pz, f, make_float2(1.0f, 1.0f));
+    return make_float2(__int_as_float(__float_as_int(pz.x) + (__float_as_int(t.x) << 23)),
+                       __int_as_float(__float_as_int(pz.y) + (__float_as_int(t.y) << 23)));
+}
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));      // not volatile: a pure function the scheduler may move
@@ -190,8 +203,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParam
                 uint32_t v[32];
                 tmem_ld32(tO + lane_off + b * 64 + c, v);
                 tc_wait_ld();
+                const float2 corr2 = make_float2(corr, corr);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) acc[c + i] = fmaf(acc[c + i], corr, __uint_as_float(v[i]));
+                for (int i = 0; i < 32; i += 2) {
+                    const float2 a2 = ffma2(make_float2(acc[c + i], acc[c + i + 1]), corr2,
+                                            make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+                    acc[c + i] = a2.x;
+                    acc[c + i + 1] = a2.y;
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -425,8 +444,14 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdPara
                 uint32_t v[32];
                 tmem_ld32(tO + lane_off + t * 64 + c, v);
                 tc_wait_ld();
+                const float2 corr2 = make_float2(corr, corr);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) acc[c + i] = fmaf(acc[c + i], corr, __uint_as_float(v[i]));
+                for (int i = 0; i < 32; i += 2) {
+                    const float2 a2 = ffma2(make_float2(acc[c + i], acc[c + i + 1]), corr2,
+                                            make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+                    acc[c + i] = a2.x;
+                    acc[c + i + 1] = a2.y;
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -442,20 +467,28 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdPara
             uint32_t v[32];
             tmem_ld32(tS + lane_off + t * 128 + c, v);
             tc_wait_ld();
-            float pv[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float sv = __uint_as_float(v[i]);
-                mxr = fmaxf(mxr, sv);
-                const float x = fmaf(sv, sc, -ref);
-                pv[i] = (i % A2_POLY_EVERY == A2_POLY_EVERY - 1) ? ex2_poly(x) : ex2_approx(x);
-                rs += pv[i];
-            }
+            // pairs of scores with packed fp32 instructions (the softmax warps are issue-bound: 57 % issue-slot utilisation with
+            // eight warps, ncu): x = s * sc - ref and the row sum as FFMA2 / FADD2, the row maximum as a 3-input max, every
+            // A2_POLY_EVERY-th PAIR of exponentials on the FMA pipe
+            const float2 sc2 = make_float2(sc, sc), nref2 = make_float2(-ref, -ref);
+            float2 rs2 = make_float2(0.f, 0.f);
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
-                const __nv_bfloat162 h2 = __floats2bfloat162_rn(pv[2 * e], pv[2 * e + 1]);
+                const float2 s2 = make_float2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+                mxr = fmaxf(fmaxf(s2.x, s2.y), mxr);
+                const float2 x2 = ffma2(s2, sc2, nref2);
+                float2 p2;
+                if (e % A2_POLY_EVERY == A2_POLY_EVERY - 1) {
+                    p2 = ex2_poly2(x2);
+                } else {
+                    p2.x = ex2_approx(x2.x);
+                    p2.y = ex2_approx(x2.y);
+                }
+                rs2 = fadd2(rs2, p2);
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(p2.x, p2.y);
                 pk[e] = *reinterpret_cast<const uint32_t*>(&h2);
             }
+            rs += rs2.x + rs2.y;
         };
         for (int j = 0; j < ntiles; ++j) {
             const uint32_t jp = j & 1;

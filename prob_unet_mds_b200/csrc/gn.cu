@@ -710,16 +710,22 @@ __device__ __forceinline__ void gn_bwd_apply_rows(const PuGnBwdArgs& a, int rows
     }
 }
 
+// one warp per channel, lanes over the samples (a serial loop over N = 64 samples per thread made each of the 73 launches
+// per step cost 16 us)
 __global__ void gn_bwd_params_kernel(PuGnBwdArgs a) {
     const PuGnArgs& f = a.f;
     const int C = f.C0 + f.C1;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (c >= C) return;
     double sad = 0.0, sbd = 0.0;
-    for (int n = 0; n < f.N; ++n) {
+    for (int n = lane; n < f.N; n += 32) {
         sad += a.sums[((long long)n * C + c) * 2];
         sbd += a.sums[((long long)n * C + c) * 2 + 1];
     }
+    sad = warp_sum_d(sad);
+    sbd = warp_sum_d(sbd);
+    if (lane != 0) return;
     const float sa = (float)sad, sb = (float)sbd;
     const float sc = f.ada ? f.ada[c] : 0.f;
     const float dg = (1.f + sc) * sb, db = (1.f + sc) * sa;
@@ -1225,7 +1231,7 @@ int pu_gn_bwd(const PuGnBwdArgs* a, void* stream) {
         gn_bwd_apply_tma_kernel<<<g2, GS_THREADS, smem, st>>>(*a, rows2, pl);
         rc = check_launch("gn_bwd_apply_tma");
         if (rc) return rc;
-        gn_bwd_params_kernel<<<cdiv(C, 128), 128, 0, st>>>(*a);
+        gn_bwd_params_kernel<<<cdiv(C, 4), 128, 0, st>>>(*a);
         return check_launch("gn_bwd_params");
     }
     if (!a->du_ready) {
@@ -1249,7 +1255,7 @@ int pu_gn_bwd(const PuGnBwdArgs* a, void* stream) {
         rc = check_launch("gn_bwd_apply");
         if (rc) return rc;
     }
-    gn_bwd_params_kernel<<<cdiv(C, 128), 128, 0, st>>>(*a);
+    gn_bwd_params_kernel<<<cdiv(C, 4), 128, 0, st>>>(*a);
     return check_launch("gn_bwd_params");
 }
 }
