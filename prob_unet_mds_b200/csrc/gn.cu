@@ -304,10 +304,32 @@ __global__ void __launch_bounds__(GN_THREADS, 3) gn_apply_kernel(PuGnArgs f, int
                 if (rr >= r1) break;
                 float x[8], o[8];
                 unpack(raw[j], x);
+                if constexpr (FAST) {
+                    // packed fp32 (FFMA2 / FMUL2): u = x * ag + bg, sigmoid(u) = 0.5 tanh(u / 2) + 0.5, silu = u * sigmoid(u)
+                    // -- this kernel is issue-bound (66 % issue-slot utilisation, ncu), not HBM-bound
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const float u = gn_u<FAST>(k, e, x[e]);
-                    o[e] = f.silu ? u * sigmoid_t<FAST>(u) : u;
+                    for (int e = 0; e < 8; e += 2) {
+                        const float2 u2 = ffma2(make_float2(x[e], x[e + 1]), make_float2(k.ag[e], k.ag[e + 1]),
+                                                make_float2(k.bg[e], k.bg[e + 1]));
+                        if (f.silu) {
+                            float t0, t1;
+                            asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(0.5f * u2.x));
+                            asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(0.5f * u2.y));
+                            const float2 s2 = ffma2(make_float2(t0, t1), make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
+                            const float2 o2 = fmul2(u2, s2);
+                            o[e] = o2.x;
+                            o[e + 1] = o2.y;
+                        } else {
+                            o[e] = u2.x;
+                            o[e + 1] = u2.y;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float u = gn_u<FAST>(k, e, x[e]);
+                        o[e] = f.silu ? u * sigmoid_t<FAST>(u) : u;
+                    }
                 }
                 if (f.dropout_p > 0.f) {
                     const long long opix = in_base + rr;
@@ -426,6 +448,33 @@ __device__ __forceinline__ void gn_du8_calc(const PuGnArgs& f, const ChanConst& 
         keep = f.keep_mask ? (uint32_t) reinterpret_cast<const uint8_t*>(f.keep_mask)[(pix * C + c0) >> 3]
                            : dropout_keep8(f.seed, (unsigned long long)((pix * C + c0) >> 3), f.dropout_p);
         inv_keep = 1.f / (1.f - f.dropout_p);
+    }
+    if constexpr (FAST) {
+        // packed fp32: xhat = x * rstd + nmr, u = x * ag + bg, d silu = s (1 + u (1 - s)) with s = 0.5 tanh(u / 2) + 0.5
+        const float2 ik2 = make_float2(inv_keep, inv_keep), one2 = make_float2(1.f, 1.f), half2 = make_float2(0.5f, 0.5f);
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+            const float2 x2 = make_float2(x[e], x[e + 1]);
+            const float2 xh2 = ffma2(x2, make_float2(k.rstd[e], k.rstd[e + 1]), make_float2(k.nmr[e], k.nmr[e + 1]));
+            xh[e] = xh2.x;
+            xh[e + 1] = xh2.y;
+            float2 gg = make_float2(((keep >> e) & 1u) ? g[e] : 0.f, ((keep >> (e + 1)) & 1u) ? g[e + 1] : 0.f);
+            if (f.silu) {
+                const float2 u2 = ffma2(x2, make_float2(k.ag[e], k.ag[e + 1]), make_float2(k.bg[e], k.bg[e + 1]));
+                float t0, t1;
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(0.5f * u2.x));
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(0.5f * u2.y));
+                const float2 s2 = ffma2(make_float2(t0, t1), half2, half2);
+                const float2 oms = ffma2(s2, make_float2(-1.f, -1.f), one2);           // 1 - s
+                const float2 d2 = fmul2(fmul2(s2, ik2), ffma2(u2, oms, one2));          // (s / keep) * (1 + u (1 - s))
+                gg = fmul2(gg, d2);
+            } else {
+                gg = fmul2(gg, ik2);
+            }
+            du[e] = gg.x;
+            du[e + 1] = gg.y;
+        }
+        return;
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
