@@ -218,12 +218,12 @@ def ncu_traffic():
             rows = [l.rstrip('\n').split('\t') for l in open(path)]
             hdr = rows[0]
             for r in rows[1:]:
-                if r[0].startswith('conv_tc_kernel<256, 1>'):
+                if r[0].startswith('conv_tc_kernel<256, 1'):      # first row: the plain 256->256 3x3 forward launch
                     rd, wr = float(r[hdr.index('dram_rd_MB')]), float(r[hdr.index('dram_wr_MB')])
                     alg = 2 * 64 * 128 * 128 * 256 * 2 / 1e6
                     return {'traffic': (rd + wr) * 1e6,
                             'traffic_source': f'committed ncu capture profiles/{name} (not measured in this run): dram '
-                                              f'read+write of one conv_tc_kernel<256,1> launch (256->256 3x3, 128x128, '
+                                              f'read+write of one conv_tc_kernel<256,1> forward launch (256->256 3x3, 128x128, '
                                               f'batch 64) = {rd + wr:.0f} MB vs {alg:.0f} MB algorithmic (input + output once)'}
         except (OSError, ValueError, IndexError):
             continue
