@@ -224,28 +224,40 @@ constexpr int A_BYTES = 128 * 128;          // 128 rows x 64 bf16
 // MT = number of 128-pixel accumulators per CTA tile.  MT = 2 (a 16x16-pixel tile, two TMA boxes sharing one weight
 // tile) is used for Cout tiles of <= 128 channels: those layers are bound by the L2 -> shared-memory operand traffic
 // (32 KB per 128x128x64 MMA block), and sharing B between two accumulators cuts it by a quarter per FLOP.
-template <int BN, int MT = 1, bool GNB = false>
+// HALO = true (3x3 only): the three taps of a filter COLUMN (dy = -1, 0, 1 at one dx) read windows of one
+// (TH + 2) x 16-pixel activation tile that start 2048 bytes (one pixel row) apart -- multiples of the 1024-byte swizzle
+// atom, so each window is an ordinary K-major SW128 operand.  One TMA box per (dx, 64-channel block) instead of three:
+// the activation bytes that cross L2 -> shared memory drop from 48 to 20 KB (MT = 1) / 96 to 36 KB (MT = 2) per three
+// 64-deep K blocks.  That feed (45 - 48 B/clk/SM with every SM streaming) is what bounds the layers whose
+// Cout tile is <= 192 channels.  Activations and weights then live in two rings with their own barriers.
+template <int BN, int MT = 1, bool GNB = false, bool HALO = false>
 struct ConvTcCfg {
     static constexpr int B_BYTES = BN * 128;
-    static constexpr int A_STAGE = MT * A_BYTES;
+    static constexpr int A_STAGE = HALO ? (TILE_H * MT + 2) * TILE_W * 128 : MT * A_BYTES;
     // GroupNorm-backward epilogue: per accumulator stage the tile's per-channel constants (float4) and sums (2 floats)
     static constexpr int GNB_BYTES = GNB ? 2 * BN * (16 + 8) : 0;
     static constexpr int MAX_STAGES = (227 * 1024 - 1280 - GNB_BYTES) / (A_STAGE + B_BYTES);
-    static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;
+    static constexpr int STAGES = MAX_STAGES > 8 ? 8 : MAX_STAGES;      // !HALO: one ring of (A, B) stages
+    static constexpr int SA = 3;                                        // HALO: activation ring ...
+    static constexpr int MAX_SB = (227 * 1024 - 1280 - GNB_BYTES - SA * A_STAGE) / B_BYTES;
+    static constexpr int SB = MAX_SB > 9 ? 9 : MAX_SB;                  // ... and weight ring (three tiles per A tile)
+    static_assert(!HALO || SB >= 4, "the weight ring needs at least four stages");
     static constexpr int ACC1 = (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
     static constexpr int ACC_STRIDE = MT * ACC1;          // one accumulator stage
     static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
     static_assert(TMEM_COLS <= 512, "two accumulator stages must fit the 512 TMEM columns");
-    static constexpr int SMEM = STAGES * (A_STAGE + B_BYTES) + 1024 /*align*/ + 256 /*barriers*/ + GNB_BYTES;
+    static constexpr int SMEM = (HALO ? SA * A_STAGE + SB * B_BYTES : STAGES * (A_STAGE + B_BYTES)) + 1024 /*align*/ +
+                                256 /*barriers*/ + GNB_BYTES;
 };
 
 // GNB = true: the epilogue is the GroupNorm-backward one (PuConvGnBwd) and nothing else (no bias / residual / ReLU)
-template <int BN, int MT, bool GNB = false>
+template <int BN, int MT, bool GNB = false, bool HALO = false>
 __global__ void __launch_bounds__(384, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const ConvTcParams p) {
-    using Cfg = ConvTcCfg<BN, MT, GNB>;
-    constexpr int STAGES = Cfg::STAGES;
+    using Cfg = ConvTcCfg<BN, MT, GNB, HALO>;
+    constexpr int STAGES = HALO ? Cfg::SA : Cfg::STAGES;      // stages of the activation ring (= the only ring if !HALO)
+    constexpr int BSTAGES = HALO ? Cfg::SB : Cfg::STAGES;     // stages of the weight ring
     constexpr int A_STAGE = Cfg::A_STAGE;
     constexpr int TH = TILE_H * MT;              // tile height in pixels
     extern __shared__ uint8_t smem_raw[];
@@ -253,12 +265,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // __shared__ symbol, so that plain C++ accesses below compile to LDS / STS instead of generic LD / ST
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_STAGE;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::B_BYTES);
-    uint64_t* full = bars;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + BSTAGES * Cfg::B_BYTES);
+    uint64_t* full = bars;                        // activation ring (and weights, if !HALO)
     uint64_t* empty = bars + STAGES;
     uint64_t* tfull = bars + 2 * STAGES;
     uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* fullB = tempty + 2;                 // HALO: weight ring
+    uint64_t* emptyB = fullB + BSTAGES;
+    static_assert(2 * STAGES + 4 + (HALO ? 2 * BSTAGES : 0) <= 30, "barriers must fit the 256-byte block");
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
     float4* gnb_consts = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2][BN]   (GNB only)
     float* gnb_sums = reinterpret_cast<float*>(gnb_consts + 2 * BN);                          // [2][BN][2]
 
@@ -274,6 +289,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(smem_u32(&full[s]), 1);
             mbar_init(smem_u32(&empty[s]), 1);
+        }
+        if constexpr (HALO) {
+            for (int s = 0; s < BSTAGES; ++s) {
+                mbar_init(smem_u32(&fullB[s]), 1);
+                mbar_init(smem_u32(&emptyB[s]), 1);
+            }
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&tfull[s]), 1);
@@ -292,8 +313,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
     if (warp == 0) {
         if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
+            int stage = 0, bstage = 0;
+            uint32_t phase = 0, bphase = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int n_tile = tile % p.n_tiles;
                 int t = tile / p.n_tiles;
@@ -302,6 +323,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 const int ty = t % p.tiles_y;
                 const int img = t / p.tiles_y;
                 const int x0 = tx * TILE_W, y0 = ty * TH, n0 = n_tile * BN;
+                if constexpr (HALO) {
+                    // per (dx, 64-channel block): one (TH + 2) x 16-pixel activation box, then the weight tiles of its
+                    // three taps (dy = -1, 0, 1)
+                    for (int g = 0; g < 3 * p.cblks; ++g) {
+                        const int dxi = g / p.cblks;
+                        const int cb = g - dxi * p.cblks;
+                        mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+                        const uint32_t fa = smem_u32(&full[stage]);
+                        mbar_expect_tx(fa, A_STAGE);
+                        const uint32_t dstA = smem_u32(sA + stage * A_STAGE);
+                        if (cb < p.cblk0)
+                            tma_load_4d(dstA, &tmA0, fa, cb * 64, x0 + dxi - 1, y0 - 1, img);
+                        else
+                            tma_load_4d(dstA, &tmA1, fa, (cb - p.cblk0) * 64, x0 + dxi - 1, y0 - 1, img);
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+#pragma unroll 1
+                        for (int t3 = 0; t3 < 3; ++t3) {
+                            const int kbw = (t3 * 3 + dxi) * p.cblks + cb;      // K block of tap (dy = t3 - 1, dx) in the weights
+                            mbar_wait(smem_u32(&emptyB[bstage]), bphase ^ 1);
+                            const uint32_t fbb = smem_u32(&fullB[bstage]);
+                            mbar_expect_tx(fbb, Cfg::B_BYTES);
+                            tma_load_2d(smem_u32(sB + bstage * Cfg::B_BYTES), &tmB, fbb, kbw * 64, n0);
+                            if (++bstage == BSTAGES) {
+                                bstage = 0;
+                                bphase ^= 1;
+                            }
+                        }
+                    }
+                    continue;
+                }
                 for (int kb = 0; kb < p.nkb; ++kb) {
                     const int tap = kb / p.cblks;
                     const int cb = kb - tap * p.cblks;
@@ -330,14 +384,52 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         {   // the whole warp runs the issue loop (warp-uniform operands stay in uniform registers; a lane-0 branch made
             // ptxas emit an ELECT/R2UR waterfall per MMA); mma_f16_ss / mma_commit elect one lane internally
             constexpr uint32_t IDESC = idesc_bf16_f32(128, BN, 0, 0);
-            int stage = 0;
-            uint32_t phase = 0;
+            int stage = 0, bstage = 0;
+            uint32_t phase = 0, bphase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 mbar_wait(smem_u32(&tempty[acc]), acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_STRIDE;
+                if constexpr (HALO) {
+                    for (int g = 0; g < 3 * p.cblks; ++g) {
+                        mbar_wait(smem_u32(&full[stage]), phase);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(sA + stage * A_STAGE);
+#pragma unroll 1
+                        for (int t3 = 0; t3 < 3; ++t3) {
+                            mbar_wait(smem_u32(&fullB[bstage]), bphase);
+                            tc_fence_after();
+                            const uint32_t b_addr = smem_u32(sB + bstage * Cfg::B_BYTES);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t bd = smem_desc_sw128(b_addr + k * 32, 16, 1024);
+#pragma unroll
+                                for (int m = 0; m < MT; ++m) {
+                                    // window of accumulator m, tap dy = t3 - 1: pixel rows [8 m + t3, +8) of the halo tile
+                                    const uint64_t ad =
+                                        smem_desc_sw128(a_addr + (m * TILE_H + t3) * (TILE_W * 128) + k * 32, 16, 1024);
+                                    mma_f16_ss(d_tmem + m * Cfg::ACC1, ad, bd, IDESC, (g | t3 | k) ? 1u : 0u);
+                                }
+                            }
+                            mma_commit(smem_u32(&emptyB[bstage]));
+                            if (++bstage == BSTAGES) {
+                                bstage = 0;
+                                bphase ^= 1;
+                            }
+                        }
+                        mma_commit(smem_u32(&empty[stage]));
+                        if (++stage == STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    mma_commit(smem_u32(&tfull[acc]));
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1;
+                    continue;
+                }
                 for (int kb = 0; kb < p.nkb; ++kb) {
                     mbar_wait(smem_u32(&full[stage]), phase);
                     tc_fence_after();
@@ -1046,12 +1138,16 @@ bool conv_tc_applicable(const PuConvArgs* a) {
     return true;
 }
 
-template <int BN, int MT, bool GNB = false>
+template <int BN, int MT, bool GNB = false, bool HALO = false>
 static int conv_tc_launch_bn(const PuConvArgs* a, cudaStream_t st) {
     if constexpr (!GNB) {
-        if (a->gn_bwd) return conv_tc_launch_bn<BN, MT, true>(a, st);
+        if (a->gn_bwd) return conv_tc_launch_bn<BN, MT, true, HALO>(a, st);
     }
-    using Cfg = ConvTcCfg<BN, MT, GNB>;
+    if constexpr (!HALO) {
+        static const bool halo_on = !(getenv("PU_CONV_HALO") && getenv("PU_CONV_HALO")[0] == '0');   // A/B switch
+        if (a->ksize == 3 && halo_on) return conv_tc_launch_bn<BN, MT, GNB, true>(a, st);
+    }
+    using Cfg = ConvTcCfg<BN, MT, GNB, HALO>;
     ConvTcParams p;
     p.N = a->N; p.H = a->H; p.W = a->W; p.Cout = a->Cout; p.ksize = a->ksize;
     p.cblk0 = a->C0 / 64;
@@ -1085,19 +1181,20 @@ static int conv_tc_launch_bn(const PuConvArgs* a, cudaStream_t st) {
     }
 
     CUtensorMap tA0, tA1, tB;
-    int rc = make_act_tmap(&tA0, a->src0, a->N, a->H, a->W, a->C0, TILE_W, TILE_H);
+    const int box_h = HALO ? TILE_H * MT + 2 : TILE_H;          // halo: one box holds the windows of three taps (and MT tiles)
+    int rc = make_act_tmap(&tA0, a->src0, a->N, a->H, a->W, a->C0, TILE_W, box_h);
     if (rc) return rc;
     if (a->C1 > 0)
-        rc = make_act_tmap(&tA1, a->src1, a->N, a->H, a->W, a->C1, TILE_W, TILE_H);
+        rc = make_act_tmap(&tA1, a->src1, a->N, a->H, a->W, a->C1, TILE_W, box_h);
     else
         tA1 = tA0;
     if (rc) return rc;
     rc = make_mat_tmap(&tB, a->weight, a->Cout, (long long)a->ksize * a->ksize * (a->C0 + a->C1), BN);
     if (rc) return rc;
 
-    PU_SMEM_ATTR((conv_tc_kernel<BN, MT, GNB>), Cfg::SMEM);
+    PU_SMEM_ATTR((conv_tc_kernel<BN, MT, GNB, HALO>), Cfg::SMEM);
     int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-    conv_tc_kernel<BN, MT, GNB><<<grid, 384, Cfg::SMEM, st>>>(tA0, tA1, tB, p);
+    conv_tc_kernel<BN, MT, GNB, HALO><<<grid, 384, Cfg::SMEM, st>>>(tA0, tA1, tB, p);
     return check_launch("conv_tc");
 }
 
