@@ -626,10 +626,24 @@ constexpr int AB2_SMEM = 2 * AT_TILE /*K,V*/ + 2 * 2 * AT_TILE /*Q,dO x2 stages*
 
 constexpr int AB2_THREADS = 512;
 
+// register reallocation between warpgroups (sm_90+): a warpgroup gives registers back / takes more than the launch gave it
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 // POLY: every POLY-th exponential of a thread is evaluated on the FMA pipe (ex2_poly) instead of MUFU.EX2; 0 = none.
 // MUFU instructions share the MIO queue with the STS.128 of P / dS, which is where the softmax warps stall.
-template <int POLY>
-__global__ void __launch_bounds__(AB2_THREADS, 1)
+// SW: softmax warps.  8: both 64-key halves of a tile are processed one after the other by the same two warpgroups
+// (512 threads).  16: each half has its own two warpgroups (768 threads; the control and drain warpgroups hand registers
+// to the softmax warpgroups with setmaxnreg) -- the softmax unit is latency-bound (28 % of the issue slots used with two
+// warps per scheduler), so twice the warps in flight overlap two units instead of serialising them.
+template <int POLY, int SW = 8>
+__global__ void __launch_bounds__(256 + SW * 32, 1)
 attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                     const AttnBwdParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -669,7 +683,7 @@ attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             mbar_init(smem_u32(&qd_full[s]), 1);
             mbar_init(smem_u32(&qd_empty[s]), 1);
             mbar_init(smem_u32(&sdp_full[s]), 1);
-            mbar_init(smem_u32(&pds_full[s]), 8);    // one arrive per softmax warp
+            mbar_init(smem_u32(&pds_full[s]), 8);    // one arrive per softmax warp of the half (SW = 16: the half's own 8)
             mbar_init(smem_u32(&pds_free[s]), 1);
             mbar_init(smem_u32(&dq_full[s]), 1);
             mbar_init(smem_u32(&dq_empty[s]), 4);    // one arrive per drain warp
@@ -688,6 +702,12 @@ attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320,
                    tDQ = tmem_base + 384;
 
+    // SW = 16: 768 threads x 80 registers at launch; the control warpgroup (warps 0-3) keeps 56, the drain warpgroup 40, the
+    // four softmax warpgroups take 96 each (128 x 56 + 128 x 40 + 512 x 96 = 61440).  setmaxnreg is the first
+    // statement of every role branch so that each role's code is compiled against its own register budget.
+    if (warp < 4) {
+        if constexpr (SW == 16) setmaxnreg_dec<56>();
+    }
     if (warp == 0) {
         if (lane == 0) {
             mbar_expect_tx(smem_u32(kv_full), 2 * AT_TILE);
@@ -770,7 +790,8 @@ attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             if (i + 1 < nq) issue_sdp(stage ^ 1, 1);
         }
         mma_commit(smem_u32(fin));
-    } else if (warp >= 12) {
+    } else if (warp >= 4 && warp < 8) {
+        if constexpr (SW == 16) setmaxnreg_dec<40>();
         // dQ drain warpgroup: warp quadrant q owns query rows (= TMEM lanes) [32q, 32q+32), all 64 feature columns.
         // dQ partial of tile i: TMEM -> registers -> vectorised fp32 reductions at L2 (bulk reductions by the TMA engine
         // and fragment-layout loads were measured and did not help: the L2 atomic rate is the limit either way).
@@ -782,28 +803,32 @@ attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             const int qi = (i + (int)blockIdx.x) % nq;     // same rotation as the TMA producer
             mbar_wait(smem_u32(&dq_full[b]), (i >> 1) & 1);
             tc_fence_after();
-            uint32_t v0[32], v1[32];
-            tmem_ld32(tDQ + b * 64 + lane_off, v0);
-            tmem_ld32(tDQ + b * 64 + lane_off + 32, v1);
-            tc_wait_ld();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&dq_empty[b]));
             float* dst = p.dq_acc + ((long long)row_base + qi * AT_TQ + r) * p.C + h * AT_D;
+#pragma unroll 1
+            for (int c = 0; c < AT_D; c += 16) {           // 16 columns at a time: the warpgroup runs on 40 registers
+                uint32_t v0[16];
+                tmem_ld16(tDQ + b * 64 + lane_off + c, v0);
+                tc_wait_ld();
+                if (c == AT_D - 16) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&dq_empty[b]));
+                }
 #pragma unroll
-            for (int e = 0; e < 32; e += 4)
-                red_add_v4(dst + e, __uint_as_float(v0[e]), __uint_as_float(v0[e + 1]), __uint_as_float(v0[e + 2]),
-                           __uint_as_float(v0[e + 3]));
-#pragma unroll
-            for (int e = 0; e < 32; e += 4)
-                red_add_v4(dst + 32 + e, __uint_as_float(v1[e]), __uint_as_float(v1[e + 1]), __uint_as_float(v1[e + 2]),
-                           __uint_as_float(v1[e + 3]));
+                for (int e = 0; e < 16; e += 4)
+                    red_add_v4(dst + c + e, __uint_as_float(v0[e]), __uint_as_float(v0[e + 1]), __uint_as_float(v0[e + 2]),
+                               __uint_as_float(v0[e + 3]));
+            }
         }
-    } else if (warp >= 4) {
-        // eight softmax warps: warp quadrant q owns query rows (= TMEM lanes) [32q, 32q+32); within a 64-key half
-        // warpgroup wg handles key columns [32wg, 32wg+32) and, for dQ / dK / dV, feature columns [32wg, 32wg+32)
+    } else if (warp >= 8) {
+        if constexpr (SW == 16) setmaxnreg_inc<96>();
+        // softmax warps: warp quadrant q owns query rows (= TMEM lanes) [32q, 32q+32); within a 64-key half warpgroup wg
+        // handles key columns [32wg, 32wg+32) and, for dK / dV, feature columns [32wg, 32wg+32).  SW = 16: warpgroups 0-1
+        // own key half 0, warpgroups 2-3 key half 1.
         const int q = warp & 3;
-        const int wg = (warp - 4) >> 2;
+        const int wgi = (warp - 8) >> 2;
+        const int wg = wgi & 1;
+        const int own_half = wgi >> 1;               // SW = 16 only
         const int r = q * 32 + lane;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
         const float sc = 0.125f * 1.4426950408889634f;
@@ -815,15 +840,49 @@ attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             mbar_wait(smem_u32(&sdp_full[half]), i & 1);
             tc_fence_after();
             const int c = half * 64 + wg * 32;
+            uint8_t* pb = sP + b * 2 * AT_TILE + half * AT_TILE + r * 128;
+            uint8_t* db = sDS + b * 2 * AT_TILE + half * AT_TILE + r * 128;
+            const int chunk0 = wg * 4;
+            if constexpr (SW == 16) {
+                // 16 columns at a time: this warpgroup runs on 104 registers
+                mbar_wait(smem_u32(&pds_free[b]), ((i >> 1) & 1) ^ 1);
+#pragma unroll
+                for (int sub = 0; sub < 2; ++sub) {
+                    uint32_t sv[16], dv[16];
+                    tmem_ld16(tS + lane_off + c + sub * 16, sv);
+                    tmem_ld16(tDP + lane_off + c + sub * 16, dv);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        uint4 pk, dk;
+                        __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&pk);
+                        __nv_bfloat162* hd = reinterpret_cast<__nv_bfloat162*>(&dk);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int i0 = g * 8 + 2 * e;
+                            const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i0]), sc, -l2));
+                            const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i0 + 1]), sc, -l2));
+                            hp[e] = __floats2bfloat162_rn(p0, p1);
+                            hd[e] = __floats2bfloat162_rn(p0 * fmaf(__uint_as_float(dv[i0]), 0.125f, -dl),
+                                                          p1 * fmaf(__uint_as_float(dv[i0 + 1]), 0.125f, -dl));
+                        }
+                        const int off = ((chunk0 + sub * 2 + g) ^ (r & 7)) << 4;
+                        *reinterpret_cast<uint4*>(pb + off) = pk;
+                        *reinterpret_cast<uint4*>(db + off) = dk;
+                    }
+                }
+                tc_fence_before();
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&pds_full[half]));
+                return;
+            }
             uint32_t sv[32], dv[32];
             tmem_ld32(tS + lane_off + c, sv);
             tmem_ld32(tDP + lane_off + c, dv);
             // the MMAs of tile i-2 must have finished reading this P / dS buffer
             if (half == 0) mbar_wait(smem_u32(&pds_free[b]), ((i >> 1) & 1) ^ 1);
             tc_wait_ld();
-            uint8_t* pb = sP + b * 2 * AT_TILE + half * AT_TILE + r * 128;
-            uint8_t* db = sDS + b * 2 * AT_TILE + half * AT_TILE + r * 128;
-            const int chunk0 = wg * 4;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 uint4 pk, dk;
@@ -853,30 +912,32 @@ attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             const int qi = (i + (int)blockIdx.x) % nq;     // same rotation as the TMA producer
             l2 = lse[qi * AT_TQ + r] * 1.4426950408889634f;
             dl = 0.125f * delta[qi * AT_TQ + r];
-            unit(i, 0);
-            unit(i, 1);
+            if constexpr (SW == 16) {
+                unit(i, own_half);
+            } else {
+                unit(i, 0);
+                unit(i, 1);
+            }
         }
         // final dV / dK: wait until every MMA of this CTA has completed
         mbar_wait(smem_u32(fin), 0);
         tc_fence_after();
         __nv_bfloat16* kp = p.dqkv + ((long long)row_base + k0 + r) * 3 * p.C + colK;
         __nv_bfloat16* vp = p.dqkv + ((long long)row_base + k0 + r) * 3 * p.C + colV;
-        {
+#pragma unroll 1
+        for (int which = 0; which < 2; ++which) {          // 0: dK, 1: dV  (SW = 16: the warpgroups of half `which` only)
+            if (SW == 16 && which != own_half) continue;
             const int c = wg * 32;
-            uint32_t a[32], b[32];
-            tmem_ld32(tDK + lane_off + c, a);
-            tmem_ld32(tDV + lane_off + c, b);
+            uint32_t a[32];
+            tmem_ld32((which == 0 ? tDK : tDV) + lane_off + c, a);
             tc_wait_ld();
+            __nv_bfloat16* op = which == 0 ? kp : vp;
 #pragma unroll
             for (int e = 0; e < 32; e += 16) {
-                float ka[16], va[16];
+                float ka[16];
 #pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                    ka[u] = __uint_as_float(a[e + u]);
-                    va[u] = __uint_as_float(b[e + u]);
-                }
-                st16(kp + c + e, ka);
-                st16(vp + c + e, va);
+                for (int u = 0; u < 16; ++u) ka[u] = __uint_as_float(a[e + u]);
+                st16(op + c + e, ka);
             }
         }
     }
@@ -1228,6 +1289,9 @@ int attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const 
     if (variant == 20) {
         PU_SMEM_ATTR(attn_bwd_tc2_kernel<0>, AB2_SMEM);
         attn_bwd_tc2_kernel<0><<<grid, AB2_THREADS, AB2_SMEM, st>>>(tm, tmdo, p);
+    } else if (variant == 4) {
+        PU_SMEM_ATTR((attn_bwd_tc2_kernel<0, 16>), AB2_SMEM);
+        attn_bwd_tc2_kernel<0, 16><<<grid, 256 + 16 * 32, AB2_SMEM, st>>>(tm, tmdo, p);
     } else if (variant == 24) {
         PU_SMEM_ATTR(attn_bwd_tc2_kernel<4>, AB2_SMEM);
         attn_bwd_tc2_kernel<4><<<grid, AB2_THREADS, AB2_SMEM, st>>>(tm, tmdo, p);

@@ -557,7 +557,7 @@ print('WORST', worst)
 """
 
 
-@pytest.mark.parametrize('variant', ['24', '3'])
+@pytest.mark.parametrize('variant', ['24', '3', '4', '20'])
 def test_attention_bwd_variants(variant):
     """The attention-backward kernels that are not the default (PU_ATTN_BWD: 24 = every 4th exponential on the FMA pipe,
     3 = transposed scores with P^T / dS^T as tensor-memory operands) against autograd, one interpreter each (the switch is
