@@ -1281,7 +1281,10 @@ int attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const 
     p.lse = lse; p.delta = delta; p.dq_acc = dq_acc;
     p.dqkv = (__nv_bfloat16*)dqkv;
     dim3 grid(T / AT_TK, N * heads);
-    // PU_ATTN_BWD (A/B runs; measured at T = 4096, heads = 4, batch 64): default = attn_bwd_tc2_kernel<0>, 4.72 - 4.75 ms;
+    // PU_ATTN_BWD (A/B runs; measured at T = 4096, heads = 4, batch 64): default = attn_bwd_tc2_kernel<0>, 4.60 - 4.75 ms;
+    // 4 = sixteen softmax warps (each key half on its own warpgroups, setmaxnreg): 5.15 ms -- more warps do not help, the
+    // iteration is a chain of MMA <-> softmax hand-offs (commit, mbarrier wake-up, tcgen05.ld, STS + fence, arrive), not a
+    // throughput limit;
     // 24 = every 4th exponential on the FMA pipe, 4.72 ms (every 2nd: 4.85 ms, removed); 3 = transposed scores
     // (attn_bwd_tc3_kernel), 5.00 ms: half the shared-memory traffic but 56 instead of 42 MIO-queue instructions (MUFU,
     // LDS, STS, LDTM / STTM) per thread and half-tile, and that queue is what the softmax warps stall on
