@@ -203,9 +203,12 @@ int pu_gn_bwd_consts(const PuGnArgs* f, float* consts, void* stream);
 int pu_attention_fwd(const void* qkv, void* out, float* lse, int N, int T, int heads, int dtype, int flags,
                      void* stream);
 /* workspaces: delta_ws fp32 [N][heads][T] (sum_d out*dout); dq_ws fp32 [N][T][C] (cross-key-tile reduction of dq,
- * only touched by the tcgen05 kernel)                                                                          */
+ * only touched by the tcgen05 kernel).  dbias (optional, fp32 [3C]) receives the column sums of dqkv over all N*T
+ * pixels -- the gradient of the qkv conv's bias (networks.py:88-89, 179) -- from the kernels' epilogues instead of a
+ * separate pass over dqkv.                                                                                       */
 int pu_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
-                     float* delta_ws, float* dq_ws, int N, int T, int heads, int dtype, int flags, void* stream);
+                     float* delta_ws, float* dq_ws, float* dbias, int N, int T, int heads, int dtype, int flags,
+                     void* stream);
 
 /* ---------------- prior / posterior encoders (prob_unet.py:32-36,60-72) ---------------- */
 /* y[N,2H,2W,C] = nearest-neighbour x2 of x (skip branch of the "up" blocks, networks.py:82-83,156) */
@@ -239,9 +242,10 @@ int pu_rsample_bwd(const float* dz, const float* eps, const float* sigma, float*
 int pu_kl_fwd_bwd(const float* mu_q, const float* ls_q, const float* mu_p, const float* ls_p, double* kl_acc,
                   float* dmu_q, float* dls_q, float* dmu_p, float* dls_p, const float* gscale, int n, void* stream);
 /* recon_acc[0] += sum (out - target)^2 over fp32 NCHW tensors (MSELoss(reduction='sum'), prob_unet.py:227);
- * dlogits (optional, NHWC [N][HW][C] in `dtype`) = *gscale * 2 * (out - target)                                */
+ * dlogits (optional, NHWC [N][HW][Cdst >= C] in `dtype`) = *gscale * 2 * (out - target) in its first C channels; the
+ * caller zero-fills the padding (3 logit channels in a 64-channel tile keep Fcomb's backward on the tensor-core kernels) */
 int pu_mse_fwd_bwd(const float* out_nchw, const float* target, double* recon_acc, void* dlogits, const float* gscale,
-                   int N, int C, int HW, int dtype, void* stream);
+                   int N, int C, int HW, int Cdst, int dtype, void* stream);
 /* (total, recon, kl) = (acc[0] + beta*acc[1], acc[0], acc[1]) as fp32 scalars (prob_unet.py:232-234) */
 int pu_loss_finalize(const double* acc, float beta, float* total, float* recon, float* kl, void* stream);
 /* out2 = (g_total + g_recon, beta*g_total + g_kl): seeds of the two loss branches from the upstream gradients

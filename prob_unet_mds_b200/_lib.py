@@ -80,8 +80,8 @@ _SIGNATURES = {
     'pu_gn_bwd': (c_int, [C.POINTER(PuGnBwdArgs), c_void_p]),
     'pu_gn_bwd_consts': (c_int, [C.POINTER(PuGnArgs), c_void_p, c_void_p]),
     'pu_attention_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    'pu_attention_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
-                                 c_int, c_int, c_int, c_void_p]),
+    'pu_attention_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                 c_int, c_int, c_int, c_int, c_void_p]),
     'pu_upsample2': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'pu_avgpool2': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'pu_relu_pool_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
@@ -95,7 +95,7 @@ _SIGNATURES = {
     'pu_rsample_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     'pu_kl_fwd_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_int, c_void_p]),
-    'pu_mse_fwd_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    'pu_mse_fwd_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'pu_loss_finalize': (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     'pu_loss_bwd_scales': (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
     'pu_fcomb_fwd': (c_int, [C.POINTER(PuFcombArgs), c_void_p]),

@@ -344,16 +344,23 @@ int pu_attention_fwd(const void* qkv, void* out, float* lse, int N, int T, int h
 }
 
 int pu_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
-                     float* delta_ws, float* dq_ws, int N, int T, int heads, int dtype, int flags, void* stream) {
+                     float* delta_ws, float* dq_ws, float* dbias, int N, int T, int heads, int dtype, int flags,
+                     void* stream) {
     PU_REQUIRE(qkv && out && dout && lse && dqkv && delta_ws && dq_ws && N > 0 && T > 0 && heads > 0,
                "pu_attention_bwd: bad arguments");
     PU_REQUIRE(dtype == PU_F32 || dtype == PU_BF16, "pu_attention_bwd: bad dtype");
     cudaStream_t st = (cudaStream_t)stream;
     int rc = pu::attention_delta(out, dout, delta_ws, N, T, heads, dtype, st);
     if (rc) return rc;
-    if (!(flags & PU_CONV_FORCE_SIMPLE) && pu::attention_bwd_tc_applicable(N, T, heads, dtype))
-        return pu::attention_bwd_tc(qkv, dout, lse, delta_ws, dqkv, dq_ws, N, T, heads, st);
-    PU_REQUIRE(!(flags & PU_CONV_FORCE_TC), "pu_attention_bwd: tcgen05 kernel does not apply (T=%d dtype=%d)", T, dtype);
-    return pu::attention_bwd_simple(qkv, dout, lse, delta_ws, dqkv, N, T, heads, dtype, st);
+    bool dbias_done = false;
+    if (!(flags & PU_CONV_FORCE_SIMPLE) && pu::attention_bwd_tc_applicable(N, T, heads, dtype)) {
+        rc = pu::attention_bwd_tc(qkv, dout, lse, delta_ws, dqkv, dq_ws, dbias, &dbias_done, N, T, heads, st);
+    } else {
+        PU_REQUIRE(!(flags & PU_CONV_FORCE_TC), "pu_attention_bwd: tcgen05 kernel does not apply (T=%d dtype=%d)", T, dtype);
+        rc = pu::attention_bwd_simple(qkv, dout, lse, delta_ws, dqkv, N, T, heads, dtype, st);
+    }
+    if (rc || !dbias || dbias_done) return rc;
+    // paths without the fused column sums: the separate pass
+    return pu_bias_grad(dqkv, dbias, (long long)N * T, 3 * heads * 64, dtype, 0, stream);
 }
 }

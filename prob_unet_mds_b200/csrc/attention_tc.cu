@@ -602,6 +602,7 @@ struct AttnBwdParams {
     const float* delta;
     float* dq_acc;            // [N*T][C] fp32, zeroed by the caller
     __nv_bfloat16* dqkv;      // [N*T][3C]
+    float* dbias;             // optional [3C], zeroed by the caller: column sums of dqkv (= gradient of the qkv conv's bias)
 };
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
@@ -939,6 +940,11 @@ attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
                 for (int u = 0; u < 16; ++u) ka[u] = __uint_as_float(a[e + u]);
                 st16(op + c + e, ka);
             }
+            if (p.dbias) {
+                // bias gradient of the qkv conv: column sums over this warp's 32 keys, one fp32 atomic per lane
+                const float tot = warp_reduce_scatter32([&](int j) { return __uint_as_float(a[j]); }, lane);
+                atomicAdd(p.dbias + (which == 0 ? colK : colV) + c + lane, tot);
+            }
         }
     }
 
@@ -1251,24 +1257,44 @@ attn_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     }
 }
 
-// dqkv[row][0:C] = bf16(dq_acc[row][:])
-__global__ void attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, long long rows,
-                                       int C) {
-    const int nvec = C / 8;
-    const long long total = rows * nvec;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int v = (int)(i % nvec);
-        const long long row = i / nvec;
-        float x[8];
-        ld8(acc + row * C + v * 8, x);
-        st8(dqkv + row * 3 * C + v * 8, x);
+// dqkv[row][0:C] = bf16(dq_acc[row][:]); optionally dbias[0:C] += column sums (the q part of the qkv bias gradient).
+// Thread (v, pl): channel vector v = tid % nvec, row lane pl = tid / nvec; a block walks `rows_per_block` rows.
+__global__ void __launch_bounds__(256)
+attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, long long rows, int C,
+                       int rows_per_block, float* __restrict__ dbias) {
+    __shared__ float cs[2048];     // C = 64 heads <= 2048 (nvec = C / 8 <= 256 threads)
+    const int nvec = C / 8, PL = 256 / nvec;
+    const int v = threadIdx.x % nvec, pl = threadIdx.x / nvec;
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    const long long r1 = min(rows, r0 + rows_per_block);
+    for (int i = threadIdx.x; i < C; i += blockDim.x) cs[i] = 0.f;
+    __syncthreads();
+    if (pl < PL) {
+        float s[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s[e] = 0.f;
+        for (long long row = r0 + pl; row < r1; row += PL) {
+            float x[8];
+            ld8(acc + row * C + v * 8, x);
+            st8(dqkv + row * 3 * C + v * 8, x);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s[e] += x[e];
+        }
+        if (dbias) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) atomicAdd(&cs[v * 8 + e], s[e]);
+        }
+    }
+    if (dbias) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dbias + i, cs[i]);
     }
 }
 
 bool attention_bwd_tc_applicable(int N, int T, int heads, int dtype) { return attention_tc_applicable(N, T, heads, dtype); }
 
 int attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv,
-                     float* dq_acc, int N, int T, int heads, cudaStream_t st) {
+                     float* dq_acc, float* dbias, bool* dbias_done, int N, int T, int heads, cudaStream_t st) {
     const int C = heads * AT_D;
     CUtensorMap tm, tmdo;
     int rc = make_mat_tmap(&tm, qkv, (long long)N * T, 3LL * C, 128);
@@ -1289,6 +1315,12 @@ int attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const 
     // (attn_bwd_tc3_kernel), 5.00 ms: half the shared-memory traffic but 56 instead of 42 MIO-queue instructions (MUFU,
     // LDS, STS, LDTM / STTM) per thread and half-tile, and that queue is what the softmax warps stall on
     static const int variant = getenv("PU_ATTN_BWD") ? atoi(getenv("PU_ATTN_BWD")) : 20;
+    // the fused qkv bias gradient (column sums of dqkv) is produced by attn_bwd_tc2_kernel's epilogue and the dQ convert
+    // kernel; the transposed-score variant leaves it to the caller's separate pass
+    const bool fuse_bias = dbias != nullptr && variant != 3 && C <= 2048;
+    p.dbias = fuse_bias ? dbias : nullptr;
+    if (fuse_bias) PU_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * 3 * C, st));
+    if (dbias_done) *dbias_done = fuse_bias;
     if (variant == 20) {
         PU_SMEM_ATTR(attn_bwd_tc2_kernel<0>, AB2_SMEM);
         attn_bwd_tc2_kernel<0><<<grid, AB2_THREADS, AB2_SMEM, st>>>(tm, tmdo, p);
@@ -1304,10 +1336,10 @@ int attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const 
     }
     rc = check_launch("attn_bwd_tc");
     if (rc) return rc;
-    long long total = (long long)N * T * (C / 8);
-    long long g = cdivll(total, 256);
-    if (g > 148 * 16) g = 148 * 16;
-    attn_dq_convert_kernel<<<(unsigned)g, 256, 0, st>>>(dq_acc, (__nv_bfloat16*)dqkv, (long long)N * T, C);
+    const long long rows = (long long)N * T;
+    int rpb = (int)cdivll(rows, 148 * 8);
+    if (rpb < 32) rpb = 32;
+    attn_dq_convert_kernel<<<(unsigned)cdivll(rows, rpb), 256, 0, st>>>(dq_acc, (__nv_bfloat16*)dqkv, rows, C, rpb, p.dbias);
     return check_launch("attn_dq_convert");
 }
 

@@ -10,6 +10,7 @@ int attention_bwd_simple(const void* qkv, const void* dout, const float* lse, co
 bool attention_tc_applicable(int N, int T, int heads, int dtype);
 bool attention_bwd_tc_applicable(int N, int T, int heads, int dtype);
 int attention_fwd_tc(const void* qkv, void* out, float* lse, int N, int T, int heads, cudaStream_t st);
+// dbias (optional, [3C] fp32): column sums of dqkv; *dbias_done says whether the kernels produced it
 int attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv,
-                     float* dq_acc, int N, int T, int heads, cudaStream_t st);
+                     float* dq_acc, float* dbias, bool* dbias_done, int N, int T, int heads, cudaStream_t st);
 }  // namespace pu

@@ -169,6 +169,32 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     return v;
 }
 
+// Sums each of 32 per-lane values val(0..31) over the 32 lanes of the warp with 31 shuffles (recursive halving: at every step
+// a lane keeps one half of its values and hands the other half to its partner).
+// Returns the warp total of val(lane).  The values are produced on demand by `val`, so only 16 of them are live at a time.
+template <typename F>
+__device__ __forceinline__ float warp_reduce_scatter32(F&& val, int lane) {
+    float v[16];
+    {
+        const bool up = (lane & 16) != 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float a = val(i), b = val(i + 16);
+            v[i] = (up ? b : a) + __shfl_xor_sync(0xffffffffu, up ? a : b, 16);
+        }
+    }
+#pragma unroll
+    for (int h = 8; h >= 1; h >>= 1) {
+        const bool up = (lane & h) != 0;
+#pragma unroll
+        for (int i = 0; i < h; ++i) {
+            const float send = up ? v[i] : v[i + h];
+            const float keep = up ? v[i + h] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+        }
+    }
+    return v[0];
+}
 // ---- Philox4x32 counter RNG (dropout masks are regenerated in backward from (seed, index)) ----
 // 7 rounds: the smallest round count that passes BigCrush (Salmon et al., SC'11); the usual 10 is a safety margin that
 // a dropout mask does not need, and the mask generation is ~1/4 of the instructions of the GroupNorm kernels.

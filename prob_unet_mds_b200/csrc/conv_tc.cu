@@ -187,31 +187,6 @@ __device__ __forceinline__ float warp_reduce_scatter16(float (&v)[16], int lane)
     }
     return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
-// The same for 32 values val(0..31) (31 shuffles): returns the warp total of val(lane).  The values are produced on
-// demand by `val`, so only 16 of them are live at a time.
-template <typename F>
-__device__ __forceinline__ float warp_reduce_scatter32(F&& val, int lane) {
-    float v[16];
-    {
-        const bool up = (lane & 16) != 0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float a = val(i), b = val(i + 16);
-            v[i] = (up ? b : a) + __shfl_xor_sync(0xffffffffu, up ? a : b, 16);
-        }
-    }
-#pragma unroll
-    for (int h = 8; h >= 1; h >>= 1) {
-        const bool up = (lane & h) != 0;
-#pragma unroll
-        for (int i = 0; i < h; ++i) {
-            const float send = up ? v[i] : v[i + h];
-            const float keep = up ? v[i + h] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
-        }
-    }
-    return v[0];
-}
 __device__ __forceinline__ float sigmoid_fast(float u) {       // 0.5 tanh(u/2) + 0.5, one MUFU (as gn.cu's bf16 kernels)
     float t;
     asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * u));

@@ -236,7 +236,7 @@ __global__ void kl_kernel(const float* __restrict__ mu_q, const float* __restric
 // recon += sum (out - target)^2 ; dlogits (NHWC, dtype) = gscale * 2 (out - target)
 template <typename T>
 __global__ void mse_kernel(const float* __restrict__ out_nchw, const float* __restrict__ target, double* __restrict__ recon,
-                           T* __restrict__ dlogits, const float* gscale_ptr, int N, int C, int HW) {
+                           T* __restrict__ dlogits, const float* gscale_ptr, int N, int C, int HW, int Cdst) {
     __shared__ double part[32];
     const float gscale = gscale_ptr ? *gscale_ptr : 1.f;
     double acc = 0.0;
@@ -249,7 +249,7 @@ __global__ void mse_kernel(const float* __restrict__ out_nchw, const float* __re
             const long long t = i / HW;
             const int c = (int)(t % C);
             const int n = (int)(t / C);
-            stf(dlogits + ((long long)n * HW + hw) * C + c, gscale * 2.f * d);
+            stf(dlogits + ((long long)n * HW + hw) * Cdst + c, gscale * 2.f * d);
         }
     }
     acc = warp_sum_d(acc);
@@ -386,16 +386,18 @@ int pu_kl_fwd_bwd(const float* mu_q, const float* ls_q, const float* mu_p, const
 }
 
 int pu_mse_fwd_bwd(const float* out_nchw, const float* target, double* recon_acc, void* dlogits, const float* gscale,
-                   int N, int C, int HW, int dtype, void* stream) {
-    PU_REQUIRE(out_nchw && target && recon_acc && N > 0 && C > 0 && HW > 0, "pu_mse_fwd_bwd: bad arguments");
+                   int N, int C, int HW, int Cdst, int dtype, void* stream) {
+    PU_REQUIRE(out_nchw && target && recon_acc && N > 0 && C > 0 && HW > 0 && (!dlogits || Cdst >= C),
+               "pu_mse_fwd_bwd: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     long long total = (long long)N * C * HW;
     unsigned grid = grid_for(total);
     if (grid > 592) grid = 592;
     if (dtype == PU_F32)
-        mse_kernel<float><<<grid, 256, 0, st>>>(out_nchw, target, recon_acc, (float*)dlogits, gscale, N, C, HW);
+        mse_kernel<float><<<grid, 256, 0, st>>>(out_nchw, target, recon_acc, (float*)dlogits, gscale, N, C, HW, Cdst);
     else
-        mse_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(out_nchw, target, recon_acc, (__nv_bfloat16*)dlogits, gscale, N, C, HW);
+        mse_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(out_nchw, target, recon_acc, (__nv_bfloat16*)dlogits, gscale, N, C, HW,
+                                                        Cdst);
     return check_launch("mse");
 }
 

@@ -383,8 +383,7 @@ class UNetEngine:
             grads[id(blk.proj.bias)] = self._colsum(dz)
             datt = ops.conv2d(dz, self.w_dgrad(blk.proj.weight), Cout, 1)
             self._wgrad(grads, blk.proj.weight, rec['att'], dz, 1)
-            dqkv = ops.attention_bwd(rec['qkv'], rec['att'], datt, rec['lse'], heads)
-            dbq = ops.bias_grad(dqkv)
+            dqkv, dbq = ops.attention_bwd(rec['qkv'], rec['att'], datt, rec['lse'], heads, want_dbias=True)
             gq = grads.alloc(blk.qkv.bias)
             ops.scatter(dbq, perm, gq)
             grads[id(blk.qkv.bias)] = gq

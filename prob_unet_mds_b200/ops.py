@@ -275,16 +275,19 @@ def attention_fwd(qkv, heads, flags=0):
     return out, lse
 
 
-def attention_bwd(qkv, out, dout, lse, heads, flags=0):
+def attention_bwd(qkv, out, dout, lse, heads, flags=0, want_dbias=False):
+    """want_dbias: also return the fp32 [3C] column sums of dqkv (the qkv conv's bias gradient, in the product's channel
+    order), taken in the kernels' epilogues."""
     N = qkv.shape[0]
     C3 = qkv.shape[-1]
     T = qkv.numel() // (N * C3)
     dqkv = torch.empty_like(qkv)
     delta = torch.empty((N, heads, T), dtype=torch.float32, device=qkv.device)
     dq_ws = torch.empty((N, T, C3 // 3), dtype=torch.float32, device=qkv.device)
-    check(lib().pu_attention_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(dqkv), ptr(delta), ptr(dq_ws), N, T,
-                                 heads, dtype_code(qkv.dtype), flags, stream_ptr()), 'attention_bwd')
-    return dqkv
+    dbias = torch.empty(C3, dtype=torch.float32, device=qkv.device) if want_dbias else None
+    check(lib().pu_attention_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(dqkv), ptr(delta), ptr(dq_ws), ptr(dbias),
+                                 N, T, heads, dtype_code(qkv.dtype), flags, stream_ptr()), 'attention_bwd')
+    return (dqkv, dbias) if want_dbias else dqkv
 
 
 # ----------------------------------------------------------------------------- encoder glue
@@ -372,12 +375,14 @@ def kl_fwd_bwd(mu_q, ls_q, mu_p, ls_p, kl_acc, gscale=None, want_grads=True):
     return g
 
 
-def mse_fwd_bwd(out_nchw, target, recon_acc, dtype=None, gscale=None):
+def mse_fwd_bwd(out_nchw, target, recon_acc, dtype=None, gscale=None, Cdst=None):
+    """Cdst: channel count of the returned dlogits tensor (>= C, zero padded)."""
     N, Cc, H, W = out_nchw.shape
+    Cdst = Cdst or Cc
     dlogits = None
     if dtype is not None:
-        dlogits = torch.empty((N, H, W, Cc), dtype=dtype, device=out_nchw.device)
-    check(lib().pu_mse_fwd_bwd(ptr(out_nchw), ptr(target), ptr(recon_acc), ptr(dlogits), ptr(gscale), N, Cc, H * W,
+        dlogits = (zeros if Cdst != Cc else torch.empty)((N, H, W, Cdst), dtype=dtype, device=out_nchw.device)
+    check(lib().pu_mse_fwd_bwd(ptr(out_nchw), ptr(target), ptr(recon_acc), ptr(dlogits), ptr(gscale), N, Cc, H * W, Cdst,
                                dtype_code(dtype) if dtype is not None else 0, stream_ptr()), 'mse')
     return dlogits
 

@@ -312,14 +312,24 @@ class _ElboFunction(torch.autograd.Function):
         scales = ops.loss_bwd_scales(g_total, g_recon, g_kl, model.beta, dev)
         # reconstruction branch: d recon / d logits, then Fcomb backward (prob_unet.py:224-227)
         scratch = ops.zeros_f64(2, dev)
-        dlogits = ops.mse_fwd_bwd(s['out'], s['target'], scratch[0:1], dtype=dt, gscale=scales[0:1])
         feat, h1, h2 = s['feat'], s['h1'], s['h2']
+        nc = w2p.shape[0]
+        # the num_classes (3) logit channels are carried in a zero-padded 64-channel tile where the tensor-core kernels
+        # apply, so that layer 2's weight and data gradients do not run on the CUDA-core kernels
+        Cp = 64 if (nc < 64 and ops.conv_tc_applies(feat, 0, 64)) else nc
+        dlogits = ops.mse_fwd_bwd(s['out'], s['target'], scratch[0:1], dtype=dt, gscale=scales[0:1], Cdst=Cp)
         # layer 2: 64 -> num_classes
         g = grads.alloc(w2p)
-        ops.unpack_wgrad(ops.conv2d_wgrad(h2, dlogits, 1), g)
+        ops.unpack_wgrad(ops.conv2d_wgrad(h2, dlogits, 1), g)          # rows beyond num_classes are padding and ignored
         grads[id(w2p)] = g
-        grads[id(b2p)] = ops.bias_grad(dlogits, db=grads.alloc(b2p))
-        dh2 = ops.conv2d(dlogits, ops.pack_weight(w2, 1, dt), 64, 1)
+        if Cp != nc:
+            grads[id(b2p)] = ops.clone(ops.bias_grad(dlogits)[:nc].contiguous(), out=grads.alloc(b2p))
+            w2pad = ops.zeros((Cp, 64, 1, 1), torch.float32, dev)
+            ops.clone(w2.reshape(-1), out=w2pad.reshape(-1)[:w2.numel()])
+            dh2 = ops.conv2d(dlogits, ops.pack_weight(w2pad, 1, dt), 64, 1)
+        else:
+            grads[id(b2p)] = ops.bias_grad(dlogits, db=grads.alloc(b2p))
+            dh2 = ops.conv2d(dlogits, ops.pack_weight(w2, 1, dt), 64, 1)
         dpre2 = ops.relu_mask(dh2, h2, out=dh2)
         # layer 1: 64 -> 64
         g = grads.alloc(w1p)

@@ -511,7 +511,8 @@ def test_attention_simple(N, T, heads, dtype):
     out, lse = ops.attention_fwd(qkv.detach().to(dt), heads, flags=L.CONV_FORCE_SIMPLE)
     tol = 1e-5 if dtype == 'f32' else 6e-3
     assert rel_err(out, ref) < tol
-    dqkv = ops.attention_bwd(qkv.detach().to(dt), out, dout.to(dt), lse, heads, flags=L.CONV_FORCE_SIMPLE)
+    dqkv, dbias = ops.attention_bwd(qkv.detach().to(dt), out, dout.to(dt), lse, heads, flags=L.CONV_FORCE_SIMPLE, want_dbias=True)
+    assert rel_err(dbias, dqkv.float().reshape(-1, dqkv.shape[-1]).sum(0)) < 1e-5      # CUDA-core path: the separate pass
     assert rel_err(dqkv, qkv.grad) < (1e-4 if dtype == 'f32' else 1.5e-2)
 
 
@@ -530,7 +531,10 @@ def test_attention_tc(N, T, heads):
     print(f'attention_tc fwd N={N} T={T} heads={heads}: rel {e:.3e}, lse max err {max_err(lse, lse_ref):.3e}')
     assert e < 6e-3
     assert max_err(lse, lse_ref) < 2e-3
-    dqkv = ops.attention_bwd(qkv.detach().to(dt), out, dout.to(dt), lse, heads)
+    dqkv, dbias = ops.attention_bwd(qkv.detach().to(dt), out, dout.to(dt), lse, heads, want_dbias=True)
+    # the fused qkv bias gradient = column sums of dqkv (taken from the fp32 accumulators, before the bf16 rounding)
+    eb_bias = rel_err(dbias, qkv.grad.reshape(-1, 3 * Cc).sum(0))
+    assert eb_bias < 5e-3, eb_bias
     eb = rel_err(dqkv, qkv.grad)
     parts = [rel_err(a, b) for a, b in zip(dqkv.float().split(Cc, dim=-1), qkv.grad.split(Cc, dim=-1))]
     print(f'attention bwd N={N} T={T} heads={heads}: rel {eb:.3e} (dq {parts[0]:.3e}, dk {parts[1]:.3e}, dv {parts[2]:.3e})')
