@@ -203,9 +203,10 @@ int pu_gn_bwd_consts(const PuGnArgs* f, float* consts, void* stream);
 int pu_attention_fwd(const void* qkv, void* out, float* lse, int N, int T, int heads, int dtype, int flags,
                      void* stream);
 /* workspaces: delta_ws fp32 [N][heads][T] (sum_d out*dout); dq_ws fp32 [N][T][C] (cross-key-tile reduction of dq,
- * only touched by the tcgen05 kernel).  dbias (optional, fp32 [3C]) receives the column sums of dqkv over all N*T
- * pixels -- the gradient of the qkv conv's bias (networks.py:88-89, 179) -- from the kernels' epilogues instead of a
- * separate pass over dqkv.                                                                                       */
+ * only touched by the tcgen05 kernel; tile-major inside) followed, when dbias != NULL, by N*heads*ceil(T/128)*192
+ * more floats (per-CTA partial column sums).  dbias (optional, fp32 [3C]) receives the column sums of dqkv over all
+ * N*T pixels -- the gradient of the qkv conv's bias (networks.py:88-89, 179) -- from the kernels' epilogues instead
+ * of a separate pass over dqkv.                                                                                   */
 int pu_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                      float* delta_ws, float* dq_ws, float* dbias, int N, int T, int heads, int dtype, int flags,
                      void* stream);

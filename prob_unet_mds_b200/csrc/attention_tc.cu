@@ -303,6 +303,7 @@ constexpr int A2_KV_STAGES = 3;
 #endif
 constexpr int A2_SMEM = 2 * AT_TILE /*Q0,Q1*/ + A2_KV_STAGES * 2 * AT_TILE /*K,V*/ + 1024 + 256;
 
+template <int ABL = 0>
 __global__ void __launch_bounds__(384, 1)
 attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -441,6 +442,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdPara
             tc_fence_after();
 #pragma unroll
             for (int c = 0; c < AT_D; c += 32) {
+                if ((ABL == 1 || ABL == 5) && jj != ntiles - 1) continue;      // ablation: no per-tile read-back of O
                 uint32_t v[32];
                 tmem_ld32(tO + lane_off + t * 64 + c, v);
                 tc_wait_ld();
@@ -478,7 +480,9 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdPara
                 mxr = fmaxf(fmaxf(s2.x, s2.y), mxr);
                 const float2 x2 = ffma2(s2, sc2, nref2);
                 float2 p2;
-                if (e % A2_POLY_EVERY == A2_POLY_EVERY - 1) {
+                if (ABL == 2) {
+                    p2 = x2;
+                } else if (e % A2_POLY_EVERY == A2_POLY_EVERY - 1) {
                     p2 = ex2_poly2(x2);
                 } else {
                     p2.x = ex2_approx(x2.x);
@@ -498,6 +502,15 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdPara
             bool exact = (j == 0);
             uint32_t pkA[16];
             if (j > 0) accumulate(j - 1, corr_prev);          // P_{j-1} consumed: the P columns may be overwritten
+            if (ABL == 5) {                                    // ablation: synchronisation chain + MMAs only
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(smem_u32(&s_empty[t]));
+                    mbar_arrive(smem_u32(&p_full[t]));
+                }
+                continue;
+            }
             if (!exact) {
 #pragma unroll 1
                 for (int c = 0; c < AT_TK; c += 32) {
@@ -578,9 +591,21 @@ int attention_fwd_tc(const void* qkv, void* out, float* lse, int N, int T, int h
     p.out = (__nv_bfloat16*)out;
     p.lse = lse;
     if (T % (2 * AT_TQ) == 0) {
-        PU_SMEM_ATTR(attn_fwd_tc2_kernel, A2_SMEM);
         dim3 grid2(T / (2 * AT_TQ), N * heads);
-        attn_fwd_tc2_kernel<<<grid2, 384, A2_SMEM, st>>>(tm, p);
+        static const int abl = getenv("PU_ATTN_FWD_ABL") ? atoi(getenv("PU_ATTN_FWD_ABL")) : 0;
+        if (abl == 1) {
+            PU_SMEM_ATTR(attn_fwd_tc2_kernel<1>, A2_SMEM);
+            attn_fwd_tc2_kernel<1><<<grid2, 384, A2_SMEM, st>>>(tm, p);
+        } else if (abl == 2) {
+            PU_SMEM_ATTR(attn_fwd_tc2_kernel<2>, A2_SMEM);
+            attn_fwd_tc2_kernel<2><<<grid2, 384, A2_SMEM, st>>>(tm, p);
+        } else if (abl == 5) {
+            PU_SMEM_ATTR(attn_fwd_tc2_kernel<5>, A2_SMEM);
+            attn_fwd_tc2_kernel<5><<<grid2, 384, A2_SMEM, st>>>(tm, p);
+        } else {
+            PU_SMEM_ATTR(attn_fwd_tc2_kernel<0>, A2_SMEM);
+            attn_fwd_tc2_kernel<0><<<grid2, 384, A2_SMEM, st>>>(tm, p);
+        }
         return check_launch("attn_fwd_tc2");
     }
     dim3 grid(T / AT_TQ, N * heads);
@@ -603,6 +628,7 @@ struct AttnBwdParams {
     float* dq_acc;            // [N*T][C] fp32, zeroed by the caller
     __nv_bfloat16* dqkv;      // [N*T][3C]
     float* dbias;             // optional [3C], zeroed by the caller: column sums of dqkv (= gradient of the qkv conv's bias)
+    float* dbias_part;        // optional [N*heads][T/128][192]: per-CTA column sums (dq | dk | dv) instead of atomics on `dbias`
 };
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
@@ -643,7 +669,7 @@ __device__ __forceinline__ void setmaxnreg_inc() {
 // (512 threads).  16: each half has its own two warpgroups (768 threads; the control and drain warpgroups hand registers
 // to the softmax warpgroups with setmaxnreg) -- the softmax unit is latency-bound (28 % of the issue slots used with two
 // warps per scheduler), so twice the warps in flight overlap two units instead of serialising them.
-template <int POLY, int SW = 8>
+template <int POLY, int SW = 8, int ABL = 0>
 __global__ void __launch_bounds__(256 + SW * 32, 1)
 attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                     const AttnBwdParams p) {
@@ -815,6 +841,10 @@ attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
                     __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(&dq_empty[b]));
                 }
+                if (ABL & 4) {
+                    if (__uint_as_float(v0[0]) == 1.2345e-30f) red_add_v4(dst + c, 0.f, 0.f, 0.f, 0.f);     // ablation: keep the loads alive
+                    continue;
+                }
 #pragma unroll
                 for (int e = 0; e < 16; e += 4)
                     red_add_v4(dst + c + e, __uint_as_float(v0[e]), __uint_as_float(v0[e + 1]), __uint_as_float(v0[e + 2]),
@@ -878,6 +908,14 @@ attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
                 if (lane == 0) mbar_arrive(smem_u32(&pds_full[half]));
                 return;
             }
+            if (ABL & 8) {     // ablation: synchronisation chain + MMAs only
+                if (half == 0) mbar_wait(smem_u32(&pds_free[b]), ((i >> 1) & 1) ^ 1);
+                tc_fence_before();
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&pds_full[half]));
+                return;
+            }
             uint32_t sv[32], dv[32];
             tmem_ld32(tS + lane_off + c, sv);
             tmem_ld32(tDP + lane_off + c, dv);
@@ -893,14 +931,18 @@ attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
                 for (int e = 0; e < 4; ++e) {
                     const int i0 = g * 8 + 2 * e;
                     const float x0 = fmaf(__uint_as_float(sv[i0]), sc, -l2), x1 = fmaf(__uint_as_float(sv[i0 + 1]), sc, -l2);
-                    const float p0 = (POLY > 0 && (i0 % POLY) == POLY - 1) ? ex2_poly(x0) : ex2_approx(x0);
-                    const float p1 = (POLY > 0 && ((i0 + 1) % POLY) == POLY - 1) ? ex2_poly(x1) : ex2_approx(x1);
+                    const float p0 = (ABL & 2) ? x0 : (POLY > 0 && (i0 % POLY) == POLY - 1) ? ex2_poly(x0) : ex2_approx(x0);
+                    const float p1 = (ABL & 2) ? x1 : (POLY > 0 && ((i0 + 1) % POLY) == POLY - 1) ? ex2_poly(x1) : ex2_approx(x1);
                     const float d0 = p0 * fmaf(__uint_as_float(dv[i0]), 0.125f, -dl);
                     const float d1 = p1 * fmaf(__uint_as_float(dv[i0 + 1]), 0.125f, -dl);
                     hp[e] = __floats2bfloat162_rn(p0, p1);
                     hd[e] = __floats2bfloat162_rn(d0, d1);
                 }
                 const int off = ((chunk0 + g) ^ (r & 7)) << 4;
+                if (ABL & 1) {     // ablation: no STS (keep the math alive with a never-true store)
+                    if (pk.x == 0x12345678u && dk.y == 0x9abcdef0u) *reinterpret_cast<uint4*>(pb + off) = pk;
+                    continue;
+                }
                 *reinterpret_cast<uint4*>(pb + off) = pk;
                 *reinterpret_cast<uint4*>(db + off) = dk;
             }
@@ -977,6 +1019,16 @@ attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
 constexpr int AB3_LD_BYTES = 2 * AT_TQ * 4;                     // lse_i + delta_i of one q tile
 constexpr int AB3_SMEM = 2 * AT_TILE /*K,V*/ + 2 * 2 * AT_TILE /*Q,dO x2 stages*/ + 2 * 2 * AT_TILE /*dS^T x2*/ +
                          2 * AB3_LD_BYTES + 1024 + 256;
+// Cluster pairs (CL = 2).  Ablation (scripts/ablate_attn.py): without the fp32 reductions of the dQ partials this kernel
+// takes 3.05 ms instead of 5.00 ms at T = 4096 -- the 8.6 GB of red.global.add traffic per call run at the chip-wide L2
+// reduction rate (~5.9 TB/s) and nothing hides them.  Two CTAs with adjacent key tiles of one (sample, head) therefore
+// form a thread-block cluster, walk the query tiles in the same order and add their dQ partials through distributed
+// shared memory before they go to L2: CTA r keeps feature columns [32 r, +32) of every tile, writes the other 32
+// columns into its peer's receive buffer (st.shared::cluster), adds what it receives and issues HALF the reductions.
+// Flow control is two mbarrier pairs per CTA, both arrived on remotely: rx_full[b] (the peer has filled my receive
+// buffer b) and tx_credit[b] (the peer has consumed what I wrote into its buffer b).
+constexpr int AB3_RX_BYTES = 128 * 32 * 4;                      // one tile's received half: [8 vec][128 rows] x 16 B
+constexpr int AB3_SMEM_CL = AB3_SMEM + 2 * AB3_RX_BYTES;
 
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -984,6 +1036,12 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
                  : "memory");
 }
 
+// BULK = 1: the dQ partial of a tile leaves the SM as ONE 32 KB cp.reduce.async.bulk (add.f32) issued by the TMA engine from a
+// shared-memory staging buffer instead of 2048 per-lane red.global.add.v4 -- the reductions then do not queue in the LSU
+// / MIO path that the softmax warps' STS and MUFU instructions share.  The dQ workspace is tile-major for this:
+// [sample*head][q tile][16 column vectors][128 rows] x 16 B (the staging layout: conflict-free STS.128), un-permuted by
+// attn_dq_convert_tiles_kernel.
+template <int ABL = 0, int CL = 1, int BULK = 0>
 __global__ void __launch_bounds__(AB2_THREADS, 1)
 attn_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                     const AttnBwdParams p) {
@@ -1004,7 +1062,10 @@ attn_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     uint64_t* dq_full = ds_free + 2;                       // [2] per dQ accumulator
     uint64_t* dq_empty = dq_full + 2;                      // [2]
     uint64_t* fin = dq_empty + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fin + 1);
+    uint64_t* rx_full = fin + 1;                           // [2] CL = 2: the peer has filled my receive buffer b
+    uint64_t* tx_credit = rx_full + 2;                     // [2] CL = 2: the peer has consumed what I wrote into its buffer b
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tx_credit + 2);
+    uint8_t* sRX = reinterpret_cast<uint8_t*>(bars) + 256; // CL = 2: receive buffers, b at + b * AB3_RX_BYTES
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nh = blockIdx.y, n = nh / p.heads, h = nh % p.heads;
@@ -1012,6 +1073,8 @@ attn_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     const int nq = p.T / AT_TQ;
     const int row_base = n * p.T;
     const int colQ = h * AT_D, colK = p.C + h * AT_D, colV = 2 * p.C + h * AT_D;
+    // rotated start of the query-tile walk (see attn_bwd_tc2_kernel); the CTAs of a cluster share it
+    const int rot = (int)blockIdx.x - (int)blockIdx.x % CL;
     const float* lse_g = p.lse + ((long long)n * p.heads + h) * p.T;
     const float* delta_g = p.delta + ((long long)n * p.heads + h) * p.T;
 
@@ -1029,6 +1092,8 @@ attn_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             mbar_init(smem_u32(&ds_free[s]), 1);
             mbar_init(smem_u32(&dq_full[s]), 1);
             mbar_init(smem_u32(&dq_empty[s]), 4);      // one arrive per drain warp
+            mbar_init(smem_u32(&rx_full[s]), 128);     // one remote arrive per drain thread of the peer
+            mbar_init(smem_u32(&tx_credit[s]), 128);
         }
         mbar_init(smem_u32(fin), 1);
         fence_barrier_init();
@@ -1039,6 +1104,7 @@ attn_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();          // the peer's barriers are initialised before anyone arrives on them
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
     const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320,
@@ -1054,7 +1120,7 @@ attn_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
                 mbar_wait(smem_u32(&qd_empty[stage]), ((i >> 1) & 1) ^ 1);
                 const uint32_t fb = smem_u32(&qd_full[stage]);
                 mbar_expect_tx(fb, 2 * AT_TILE + AB3_LD_BYTES);
-                const int qi = (i + (int)blockIdx.x) % nq;     // rotated start: see attn_bwd_tc2_kernel
+                const int qi = (i + rot) % nq;
                 tma_load_2d(smem_u32(sQD + stage * 2 * AT_TILE), &tmQKV, fb, colQ, row_base + qi * AT_TQ);
                 tma_load_2d(smem_u32(sQD + stage * 2 * AT_TILE + AT_TILE), &tmDO, fb, colQ, row_base + qi * AT_TQ);
                 bulk_load_1d(smem_u32(sLD + stage * 2 * AT_TQ), lse_g + qi * AT_TQ, AT_TQ * 4, fb);
@@ -1138,9 +1204,14 @@ attn_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         const int q = warp & 3;
         const int r = q * 32 + lane;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+        // peer-side addresses of this thread's slots in the receive buffers and of the two remote barriers
+        const uint32_t peer_rx = CL > 1 ? mapa_cluster(smem_u32(sRX) + (uint32_t)r * 16u, crank ^ 1u) : 0u;
+        const uint32_t peer_full = CL > 1 ? mapa_cluster(smem_u32(rx_full), crank ^ 1u) : 0u;
+        const uint32_t peer_credit = CL > 1 ? mapa_cluster(smem_u32(tx_credit), crank ^ 1u) : 0u;
         for (int i = 0; i < nq; ++i) {
             const int b = i & 1;
-            const int qi = (i + (int)blockIdx.x) % nq;
+            const int qi = (i + rot) % nq;
             mbar_wait(smem_u32(&dq_full[b]), (i >> 1) & 1);
             tc_fence_after();
             uint32_t v0[32], v1[32];
@@ -1151,6 +1222,64 @@ attn_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&dq_empty[b]));
             float* dst = p.dq_acc + ((long long)row_base + qi * AT_TQ + r) * p.C + h * AT_D;
+            if constexpr (BULK) {
+                const bool issuer = (warp == 12 && lane == 0);
+                // the previous tile's bulk reduction has finished READING the staging buffer
+                if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                float4* stg = reinterpret_cast<float4*>(sRX) + r;
+#pragma unroll
+                for (int v = 0; v < 8; ++v)
+                    stg[v * 128] = make_float4(0.125f * __uint_as_float(v0[4 * v]), 0.125f * __uint_as_float(v0[4 * v + 1]),
+                                               0.125f * __uint_as_float(v0[4 * v + 2]), 0.125f * __uint_as_float(v0[4 * v + 3]));
+#pragma unroll
+                for (int v = 0; v < 8; ++v)
+                    stg[(8 + v) * 128] = make_float4(0.125f * __uint_as_float(v1[4 * v]), 0.125f * __uint_as_float(v1[4 * v + 1]),
+                                                     0.125f * __uint_as_float(v1[4 * v + 2]), 0.125f * __uint_as_float(v1[4 * v + 3]));
+                fence_proxy_async();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (issuer && !(ABL & 4)) {
+                    float* tile = p.dq_acc + (((long long)n * p.heads + h) * nq + qi) * (AT_TQ * AT_D);
+                    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(tile),
+                                 "r"(smem_u32(sRX)), "r"(AT_TQ * AT_D * 4)
+                                 : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                continue;
+            }
+            if constexpr (CL > 1) {
+                // columns [32 crank, +32) stay here, the other 32 go to the peer
+                float mine[32], theirs[32];
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {         // selects, not array references: everything stays in registers
+                    mine[e] = __uint_as_float(crank ? v1[e] : v0[e]);
+                    theirs[e] = __uint_as_float(crank ? v0[e] : v1[e]);
+                }
+                if (i >= 2) mbar_wait_cluster(smem_u32(&tx_credit[b]), ((i >> 1) - 1) & 1);   // the peer has read tile i-2
+#pragma unroll
+                for (int v = 0; v < 8; ++v)
+                    st_cluster_v4(peer_rx + (uint32_t)(b * AB3_RX_BYTES + v * 2048), theirs[4 * v], theirs[4 * v + 1],
+                                  theirs[4 * v + 2], theirs[4 * v + 3]);
+                mbar_arrive_cluster(peer_full + (uint32_t)b * 8u);
+                mbar_wait_cluster(smem_u32(&rx_full[b]), (i >> 1) & 1);
+                const float4* rx = reinterpret_cast<const float4*>(sRX + b * AB3_RX_BYTES + r * 16);
+                float* dstc = dst + 32 * (int)crank;
+#pragma unroll
+                for (int v = 0; v < 8; ++v) {
+                    const float4 o = rx[v * 128];
+                    if (!(ABL & 4))
+                        red_add_v4(dstc + 4 * v, 0.125f * (mine[4 * v] + o.x), 0.125f * (mine[4 * v + 1] + o.y),
+                                   0.125f * (mine[4 * v + 2] + o.z), 0.125f * (mine[4 * v + 3] + o.w));
+                    else if (o.x + mine[4 * v] == 1.2345e-30f)
+                        red_add_v4(dstc, 0.f, 0.f, 0.f, 0.f);
+                }
+                mbar_arrive_cluster(peer_credit + (uint32_t)b * 8u);
+                continue;
+            }
+            if (ABL & 4) {      // ablation: no reductions
+                if (__uint_as_float(v0[0]) == 1.2345e-30f && __uint_as_float(v1[0]) == 1.2345e-30f) red_add_v4(dst, 0.f, 0.f, 0.f, 0.f);
+                continue;
+            }
 #pragma unroll
             for (int e = 0; e < 32; e += 4)
                 red_add_v4(dst + e, 0.125f * __uint_as_float(v0[e]), 0.125f * __uint_as_float(v0[e + 1]),
@@ -1159,6 +1288,9 @@ attn_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             for (int e = 0; e < 32; e += 4)
                 red_add_v4(dst + 32 + e, 0.125f * __uint_as_float(v1[e]), 0.125f * __uint_as_float(v1[e + 1]),
                            0.125f * __uint_as_float(v1[e + 2]), 0.125f * __uint_as_float(v1[e + 3]));
+        }
+        if constexpr (BULK) {
+            if (warp == 12 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
     } else if (warp >= 4) {
         // eight softmax warps: warp quadrant q owns KEY rows (= TMEM lanes) [32q, 32q+32); within a 64-query half warpgroup
@@ -1174,6 +1306,17 @@ attn_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             if (half == 0) mbar_wait(smem_u32(&qd_full[b]), (i >> 1) & 1);   // lse / delta of tile i are in shared memory
             mbar_wait(smem_u32(&sdp_full[half]), i & 1);
             tc_fence_after();
+            if (ABL & 8) {     // ablation: synchronisation chain + MMAs only
+                if (half == 0) mbar_wait(smem_u32(&ds_free[b]), ((i >> 1) & 1) ^ 1);
+                tc_fence_before();
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(smem_u32(&pds_full[half]));
+                    if (half == 1) mbar_arrive(smem_u32(&qd_empty[b]));
+                }
+                return;
+            }
             uint32_t sv[32], dv[32];
             tmem_ld32(tS + lane_off + c, sv);
             tmem_ld32(tDP + lane_off + c, dv);
@@ -1185,7 +1328,14 @@ attn_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             uint32_t pk[16], dk[16];
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
-                const float4 l = l4[g], d = d4[g];         // broadcast reads: every lane of the warp wants the same columns
+                float4 l, d;
+                if (ABL & 1) {                // ablation: no LDS of the per-column constants
+                    l = make_float4(3.f, 3.f, 3.f, 3.f);
+                    d = make_float4(0.1f, 0.1f, 0.1f, 0.1f);
+                } else {
+                    l = l4[g];                             // broadcast reads: every lane of the warp wants the same columns
+                    d = d4[g];
+                }
                 const float lv[4] = {l.x, l.y, l.z, l.w}, dl[4] = {d.x, d.y, d.z, d.w};
                 float pv[4], dsv[4];
 #pragma unroll
@@ -1209,6 +1359,7 @@ attn_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 const int off = ((wg * 4 + g) ^ (r & 7)) << 4;
+                if (ABL & 2) continue;                    // ablation: no STS of dS^T
                 *reinterpret_cast<uint4*>(db + off) = make_uint4(dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
             }
             tc_wait_st();
@@ -1246,9 +1397,28 @@ attn_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
                 st16(kp + c + e, ka);
                 st16(vp + c + e, va);
             }
+            if (p.dbias_part) {
+                // bias gradient of the qkv conv (k and v parts): column sums over this CTA's 128 keys, taken from the fp32
+                // accumulators.  Warp -> lane-owned columns (reduce-scatter), the four key quadrants meet in shared memory
+                // (the lse / delta stage buffers are dead by now), one plain store per column into the per-CTA slot of
+                // the partial-sum workspace: global atomics onto the 2C addresses cost 1.3 ms per call at T = 4096
+                // (8192 CTAs x 8 warps hitting the same 512 words)
+                float* cs = sLD;                       // [0,64) dk, [64,128) dv
+                const int st = threadIdx.x - 128;      // 0..255 among the softmax warps
+                if (st < 128) cs[st] = 0.f;
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                const float tk = warp_reduce_scatter32([&](int j) { return 0.125f * __uint_as_float(a[j]); }, lane);
+                const float tv = warp_reduce_scatter32([&](int j) { return __uint_as_float(b[j]); }, lane);
+                atomicAdd(cs + c + lane, tk);
+                atomicAdd(cs + 64 + c + lane, tv);
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                if (st < 128)
+                    p.dbias_part[((long long)nh * gridDim.x + blockIdx.x) * 192 + 64 + st] = cs[st];
+            }
         }
     }
 
+    if constexpr (CL > 1) cluster_sync_all();          // no CTA leaves while its peer may still write to it
     tc_fence_before();
     __syncthreads();
     if (warp == 2) {
@@ -1291,6 +1461,75 @@ attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict_
     }
 }
 
+// the same for the tile-major workspace of the bulk-reduction variant: acc[(sample*head)][q tile][16 vec][128 rows] x 16 B.
+// One block per (q tile, sample*head): coalesced 16-byte loads (rows fastest), a shared-memory transposition, then one
+// 128-byte row segment (64 bf16) per 8 threads.
+__global__ void __launch_bounds__(256)
+attn_dq_convert_tiles_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, int T, int heads, int C,
+                             float* __restrict__ dbias_part) {
+    __shared__ float tile[128][65];
+    const int nq = T / AT_TQ;
+    const int qi = blockIdx.x, nh = blockIdx.y, n = nh / heads, h = nh % heads;
+    const float4* src = reinterpret_cast<const float4*>(acc + ((long long)nh * nq + qi) * (AT_TQ * AT_D));
+    for (int idx = threadIdx.x; idx < 16 * 128; idx += 256) {
+        const int v = idx >> 7, r = idx & 127;
+        const float4 x = src[idx];
+        tile[r][4 * v] = x.x;
+        tile[r][4 * v + 1] = x.y;
+        tile[r][4 * v + 2] = x.z;
+        tile[r][4 * v + 3] = x.w;
+    }
+    __syncthreads();
+    const int seg = threadIdx.x & 7;              // 8 columns of the row
+    float cs[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) cs[e] = 0.f;
+    for (int r = threadIdx.x >> 3; r < 128; r += 32) {
+        float x[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            x[e] = tile[r][seg * 8 + e];
+            cs[e] += x[e];
+        }
+        st8(dqkv + ((long long)n * T + qi * AT_TQ + r) * 3 * C + h * AT_D + seg * 8, x);
+    }
+    if (dbias_part) {
+        // column sums of the tile (the q part of the qkv bias gradient) into this block's slot of the partial-sum
+        // workspace: lanes with equal `seg` (stride 8 in the warp) hold partial sums of the same columns
+        __shared__ float part[8][64];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 8);
+            cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 16);
+        }
+        if ((threadIdx.x & 31) < 8) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) part[threadIdx.x >> 5][seg * 8 + e] = cs[e];
+        }
+        __syncthreads();
+        if (threadIdx.x < 64) {
+            float tot = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) tot += part[w][threadIdx.x];
+            dbias_part[((long long)nh * nq + qi) * 192 + threadIdx.x] = tot;
+        }
+    }
+}
+
+// dbias[part*C + h*64 + d] = sum over samples and tiles of the per-CTA partial sums ws[(n*heads + h)][tile][part*64 + d]
+__global__ void __launch_bounds__(192)
+attn_dbias_finish_kernel(const float* __restrict__ ws, float* __restrict__ dbias, int N, int tiles, int heads, int C) {
+    const int h = blockIdx.x, c = threadIdx.x;
+    float tot = 0.f;
+    for (int n = 0; n < N; ++n) {
+        const float* base = ws + ((long long)(n * heads + h) * tiles) * 192 + c;
+        float part = 0.f;
+        for (int t = 0; t < tiles; ++t) part += base[(long long)t * 192];
+        tot += part;
+    }
+    dbias[(c >> 6) * C + h * AT_D + (c & 63)] = tot;
+}
+
 bool attention_bwd_tc_applicable(int N, int T, int heads, int dtype) { return attention_tc_applicable(N, T, heads, dtype); }
 
 int attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv,
@@ -1314,12 +1553,17 @@ int attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const 
     // 24 = every 4th exponential on the FMA pipe, 4.72 ms (every 2nd: 4.85 ms, removed); 3 = transposed scores
     // (attn_bwd_tc3_kernel), 5.00 ms: half the shared-memory traffic but 56 instead of 42 MIO-queue instructions (MUFU,
     // LDS, STS, LDTM / STTM) per thread and half-tile, and that queue is what the softmax warps stall on
-    static const int variant = getenv("PU_ATTN_BWD") ? atoi(getenv("PU_ATTN_BWD")) : 20;
+    static const int variant = getenv("PU_ATTN_BWD") ? atoi(getenv("PU_ATTN_BWD")) : 33;
     // the fused qkv bias gradient (column sums of dqkv) is produced by attn_bwd_tc2_kernel's epilogue and the dQ convert
     // kernel; the transposed-score variant leaves it to the caller's separate pass
-    const bool fuse_bias = dbias != nullptr && variant != 3 && C <= 2048;
-    p.dbias = fuse_bias ? dbias : nullptr;
-    if (fuse_bias) PU_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * 3 * C, st));
+    // the transposed-score kernel collects per-CTA partial sums in the tail of the dQ workspace (no atomics); its
+    // non-default launch forms (3, 32) leave the bias gradient to the caller's separate pass
+    const bool tc3 = variant == 3 || (variant >= 30 && variant < 40) || variant >= 300;
+    const bool part_bias = dbias != nullptr && (variant == 33 || variant == 334);
+    const bool fuse_bias = dbias != nullptr && C <= 2048 && (!tc3 || part_bias);
+    p.dbias = (fuse_bias && !part_bias) ? dbias : nullptr;
+    p.dbias_part = part_bias ? dq_acc + (size_t)N * T * C : nullptr;
+    if (p.dbias) PU_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * 3 * C, st));
     if (dbias_done) *dbias_done = fuse_bias;
     if (variant == 20) {
         PU_SMEM_ATTR(attn_bwd_tc2_kernel<0>, AB2_SMEM);
@@ -1330,9 +1574,58 @@ int attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const 
     } else if (variant == 24) {
         PU_SMEM_ATTR(attn_bwd_tc2_kernel<4>, AB2_SMEM);
         attn_bwd_tc2_kernel<4><<<grid, AB2_THREADS, AB2_SMEM, st>>>(tm, tmdo, p);
+    }
+#define PU_ABL2(V, A)                                                             \
+    else if (variant == V) {                                                      \
+        PU_SMEM_ATTR((attn_bwd_tc2_kernel<0, 8, A>), AB2_SMEM);                    \
+        attn_bwd_tc2_kernel<0, 8, A><<<grid, AB2_THREADS, AB2_SMEM, st>>>(tm, tmdo, p); \
+    }
+#define PU_ABL3(V, A)                                                             \
+    else if (variant == V) {                                                      \
+        PU_SMEM_ATTR(attn_bwd_tc3_kernel<A>, AB3_SMEM);                            \
+        attn_bwd_tc3_kernel<A><<<grid, AB2_THREADS, AB3_SMEM, st>>>(tm, tmdo, p);   \
+    }
+    PU_ABL2(201, 1) PU_ABL2(202, 2) PU_ABL2(204, 4) PU_ABL2(208, 8) PU_ABL2(212, 12) PU_ABL2(205, 5)
+    PU_ABL3(301, 1) PU_ABL3(303, 3) PU_ABL3(304, 4) PU_ABL3(305, 5) PU_ABL3(307, 7) PU_ABL3(308, 8) PU_ABL3(312, 12)
+    else if (variant == 33 || variant == 334) {
+        // dQ partials as one TMA bulk reduction per tile; tile-major workspace
+        if (variant == 33) {
+            PU_SMEM_ATTR((attn_bwd_tc3_kernel<0, 1, 1>), AB3_SMEM_CL);
+            attn_bwd_tc3_kernel<0, 1, 1><<<grid, AB2_THREADS, AB3_SMEM_CL, st>>>(tm, tmdo, p);
+        } else {
+            PU_SMEM_ATTR((attn_bwd_tc3_kernel<4, 1, 1>), AB3_SMEM_CL);
+            attn_bwd_tc3_kernel<4, 1, 1><<<grid, AB2_THREADS, AB3_SMEM_CL, st>>>(tm, tmdo, p);
+        }
+        rc = check_launch("attn_bwd_tc3_bulk");
+        if (rc) return rc;
+        attn_dq_convert_tiles_kernel<<<dim3(T / AT_TQ, N * heads), 256, 0, st>>>(dq_acc, (__nv_bfloat16*)dqkv, T, heads, C,
+                                                                                   p.dbias_part);
+        rc = check_launch("attn_dq_convert_tiles");
+        if (rc || !part_bias) return rc;
+        attn_dbias_finish_kernel<<<heads, 192, 0, st>>>(p.dbias_part, dbias, N, T / AT_TQ, heads, C);
+        return check_launch("attn_dbias_finish");
+    }
+    else if ((variant == 32 || variant == 324) && (T / AT_TK) % 2 == 0) {
+        // cluster pairs: adjacent key tiles of one (sample, head) exchange their dQ halves through distributed shared memory
+        auto kern = variant == 32 ? attn_bwd_tc3_kernel<0, 2> : attn_bwd_tc3_kernel<4, 2>;
+        if (variant == 32) PU_SMEM_ATTR((attn_bwd_tc3_kernel<0, 2>), AB3_SMEM_CL);
+        else PU_SMEM_ATTR((attn_bwd_tc3_kernel<4, 2>), AB3_SMEM_CL);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(AB2_THREADS);
+        cfg.dynamicSmemBytes = AB3_SMEM_CL;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        PU_CUDA(cudaLaunchKernelEx(&cfg, kern, tm, tmdo, p));
     } else {
-        PU_SMEM_ATTR(attn_bwd_tc3_kernel, AB3_SMEM);
-        attn_bwd_tc3_kernel<<<grid, AB2_THREADS, AB3_SMEM, st>>>(tm, tmdo, p);
+        PU_SMEM_ATTR(attn_bwd_tc3_kernel<0>, AB3_SMEM);
+        attn_bwd_tc3_kernel<0><<<grid, AB2_THREADS, AB3_SMEM, st>>>(tm, tmdo, p);
     }
     rc = check_launch("attn_bwd_tc");
     if (rc) return rc;

@@ -283,7 +283,9 @@ def attention_bwd(qkv, out, dout, lse, heads, flags=0, want_dbias=False):
     T = qkv.numel() // (N * C3)
     dqkv = torch.empty_like(qkv)
     delta = torch.empty((N, heads, T), dtype=torch.float32, device=qkv.device)
-    dq_ws = torch.empty((N, T, C3 // 3), dtype=torch.float32, device=qkv.device)
+    # dQ accumulation workspace [N][T][C] + (want_dbias) the per-CTA column-sum partials [N*heads][ceil(T/128)][192]
+    n_ws = N * T * (C3 // 3) + (N * heads * ((T + 127) // 128) * 192 if want_dbias else 0)
+    dq_ws = torch.empty(n_ws, dtype=torch.float32, device=qkv.device)
     dbias = torch.empty(C3, dtype=torch.float32, device=qkv.device) if want_dbias else None
     check(lib().pu_attention_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(dqkv), ptr(delta), ptr(dq_ws), ptr(dbias),
                                  N, T, heads, dtype_code(qkv.dtype), flags, stream_ptr()), 'attention_bwd')

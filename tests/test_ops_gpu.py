@@ -547,7 +547,7 @@ sys.path.insert(0, {root!r})
 from prob_unet_mds_b200 import _lib as L, ops
 g = torch.Generator().manual_seed(0)
 worst = 0.0
-for (N, T, heads) in ((2, 128, 2), (1, 1024, 4), (3, 384, 6)):
+for (N, T, heads) in ((2, 128, 2), (1, 1024, 4), (3, 384, 6), (2, 256, 8), (1, 4096, 4)):
     C = heads * 64
     qkv = (torch.randn(N, T, 3 * C, generator=g) * 1.5).cuda().bfloat16().float().requires_grad_(True)
     q, k, v = [t.reshape(N, T, heads, 64).permute(0, 2, 1, 3) for t in qkv.split(C, dim=-1)]
@@ -555,17 +555,21 @@ for (N, T, heads) in ((2, 128, 2), (1, 1024, 4), (3, 384, 6)):
     dout = torch.randn(N, T, C, generator=g).cuda().bfloat16().float()
     ref.backward(dout)
     out, lse = ops.attention_fwd(qkv.detach().bfloat16(), heads, flags=L.CONV_FORCE_TC)
-    dqkv = ops.attention_bwd(qkv.detach().bfloat16(), out, dout.bfloat16(), lse, heads, flags=L.CONV_FORCE_TC)
+    dqkv, dbias = ops.attention_bwd(qkv.detach().bfloat16(), out, dout.bfloat16(), lse, heads, flags=L.CONV_FORCE_TC,
+                                    want_dbias=True)
     worst = max(worst, ((dqkv.float() - qkv.grad).norm() / qkv.grad.norm()).item())
+    bref = qkv.grad.reshape(-1, 3 * C).sum(0)
+    worst = max(worst, ((dbias - bref).norm() / bref.norm()).item())
 print('WORST', worst)
 """
 
 
-@pytest.mark.parametrize('variant', ['24', '3', '4', '20'])
+@pytest.mark.parametrize('variant', ['24', '3', '32', '33', '4', '20'])
 def test_attention_bwd_variants(variant):
     """The attention-backward kernels that are not the default (PU_ATTN_BWD: 24 = every 4th exponential on the FMA pipe,
-    3 = transposed scores with P^T / dS^T as tensor-memory operands) against autograd, one interpreter each (the switch is
-    read once per process)."""
+    3 = transposed scores with P^T / dS^T as tensor-memory operands, 32 = the same in thread-block cluster pairs that add
+    their dQ partials through distributed shared memory) against autograd, one interpreter each (the switch is read once
+    per process)."""
     import os
     import subprocess
     import sys
