@@ -303,7 +303,7 @@ constexpr int A2_KV_STAGES = 3;
 #endif
 constexpr int A2_SMEM = 2 * AT_TILE /*Q0,Q1*/ + A2_KV_STAGES * 2 * AT_TILE /*K,V*/ + 1024 + 256;
 
-template <int ABL = 0>
+template <int ABL = 0, int POLY_EVERY = A2_POLY_EVERY>
 __global__ void __launch_bounds__(384, 1)
 attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -482,7 +482,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdPara
                 float2 p2;
                 if (ABL == 2) {
                     p2 = x2;
-                } else if (e % A2_POLY_EVERY == A2_POLY_EVERY - 1) {
+                } else if (e % POLY_EVERY == POLY_EVERY - 1) {
                     p2 = ex2_poly2(x2);
                 } else {
                     p2.x = ex2_approx(x2.x);
@@ -603,8 +603,20 @@ int attention_fwd_tc(const void* qkv, void* out, float* lse, int N, int T, int h
             PU_SMEM_ATTR(attn_fwd_tc2_kernel<5>, A2_SMEM);
             attn_fwd_tc2_kernel<5><<<grid2, 384, A2_SMEM, st>>>(tm, p);
         } else {
-            PU_SMEM_ATTR(attn_fwd_tc2_kernel<0>, A2_SMEM);
-            attn_fwd_tc2_kernel<0><<<grid2, 384, A2_SMEM, st>>>(tm, p);
+            static const int poly = getenv("PU_ATTN_FWD_POLY") ? atoi(getenv("PU_ATTN_FWD_POLY")) : A2_POLY_EVERY;
+            if (poly == 1) {
+                PU_SMEM_ATTR((attn_fwd_tc2_kernel<0, 1>), A2_SMEM);
+                attn_fwd_tc2_kernel<0, 1><<<grid2, 384, A2_SMEM, st>>>(tm, p);
+            } else if (poly == 2) {
+                PU_SMEM_ATTR((attn_fwd_tc2_kernel<0, 2>), A2_SMEM);
+                attn_fwd_tc2_kernel<0, 2><<<grid2, 384, A2_SMEM, st>>>(tm, p);
+            } else if (poly == 3) {
+                PU_SMEM_ATTR((attn_fwd_tc2_kernel<0, 3>), A2_SMEM);
+                attn_fwd_tc2_kernel<0, 3><<<grid2, 384, A2_SMEM, st>>>(tm, p);
+            } else {
+                PU_SMEM_ATTR((attn_fwd_tc2_kernel<0, 4>), A2_SMEM);
+                attn_fwd_tc2_kernel<0, 4><<<grid2, 384, A2_SMEM, st>>>(tm, p);
+            }
         }
         return check_launch("attn_fwd_tc2");
     }
@@ -1019,16 +1031,8 @@ attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
 constexpr int AB3_LD_BYTES = 2 * AT_TQ * 4;                     // lse_i + delta_i of one q tile
 constexpr int AB3_SMEM = 2 * AT_TILE /*K,V*/ + 2 * 2 * AT_TILE /*Q,dO x2 stages*/ + 2 * 2 * AT_TILE /*dS^T x2*/ +
                          2 * AB3_LD_BYTES + 1024 + 256;
-// Cluster pairs (CL = 2).  Ablation (scripts/ablate_attn.py): without the fp32 reductions of the dQ partials this kernel
-// takes 3.05 ms instead of 5.00 ms at T = 4096 -- the 8.6 GB of red.global.add traffic per call run at the chip-wide L2
-// reduction rate (~5.9 TB/s) and nothing hides them.  Two CTAs with adjacent key tiles of one (sample, head) therefore
-// form a thread-block cluster, walk the query tiles in the same order and add their dQ partials through distributed
-// shared memory before they go to L2: CTA r keeps feature columns [32 r, +32) of every tile, writes the other 32
-// columns into its peer's receive buffer (st.shared::cluster), adds what it receives and issues HALF the reductions.
-// Flow control is two mbarrier pairs per CTA, both arrived on remotely: rx_full[b] (the peer has filled my receive
-// buffer b) and tx_credit[b] (the peer has consumed what I wrote into its buffer b).
-constexpr int AB3_RX_BYTES = 128 * 32 * 4;                      // one tile's received half: [8 vec][128 rows] x 16 B
-constexpr int AB3_SMEM_CL = AB3_SMEM + 2 * AB3_RX_BYTES;
+constexpr int AB3_STG_BYTES = AT_TQ * AT_D * 4;                 // dQ staging tile: [16 column vectors][128 rows] x 16 B
+constexpr int AB3_SMEM_BULK = AB3_SMEM + AB3_STG_BYTES;
 
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -1041,7 +1045,7 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
 // / MIO path that the softmax warps' STS and MUFU instructions share.  The dQ workspace is tile-major for this:
 // [sample*head][q tile][16 column vectors][128 rows] x 16 B (the staging layout: conflict-free STS.128), un-permuted by
 // attn_dq_convert_tiles_kernel.
-template <int ABL = 0, int CL = 1, int BULK = 0>
+template <int ABL = 0, int BULK = 0>
 __global__ void __launch_bounds__(AB2_THREADS, 1)
 attn_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                     const AttnBwdParams p) {
@@ -1062,10 +1066,8 @@ attn_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     uint64_t* dq_full = ds_free + 2;                       // [2] per dQ accumulator
     uint64_t* dq_empty = dq_full + 2;                      // [2]
     uint64_t* fin = dq_empty + 2;
-    uint64_t* rx_full = fin + 1;                           // [2] CL = 2: the peer has filled my receive buffer b
-    uint64_t* tx_credit = rx_full + 2;                     // [2] CL = 2: the peer has consumed what I wrote into its buffer b
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tx_credit + 2);
-    uint8_t* sRX = reinterpret_cast<uint8_t*>(bars) + 256; // CL = 2: receive buffers, b at + b * AB3_RX_BYTES
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(fin + 1);
+    uint8_t* sSTG = reinterpret_cast<uint8_t*>(bars) + 256;   // BULK: staging tile of the dQ partial
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nh = blockIdx.y, n = nh / p.heads, h = nh % p.heads;
@@ -1073,8 +1075,7 @@ attn_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     const int nq = p.T / AT_TQ;
     const int row_base = n * p.T;
     const int colQ = h * AT_D, colK = p.C + h * AT_D, colV = 2 * p.C + h * AT_D;
-    // rotated start of the query-tile walk (see attn_bwd_tc2_kernel); the CTAs of a cluster share it
-    const int rot = (int)blockIdx.x - (int)blockIdx.x % CL;
+    const int rot = (int)blockIdx.x;                       // rotated start of the query-tile walk (see attn_bwd_tc2_kernel)
     const float* lse_g = p.lse + ((long long)n * p.heads + h) * p.T;
     const float* delta_g = p.delta + ((long long)n * p.heads + h) * p.T;
 
@@ -1092,8 +1093,6 @@ attn_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
             mbar_init(smem_u32(&ds_free[s]), 1);
             mbar_init(smem_u32(&dq_full[s]), 1);
             mbar_init(smem_u32(&dq_empty[s]), 4);      // one arrive per drain warp
-            mbar_init(smem_u32(&rx_full[s]), 128);     // one remote arrive per drain thread of the peer
-            mbar_init(smem_u32(&tx_credit[s]), 128);
         }
         mbar_init(smem_u32(fin), 1);
         fence_barrier_init();
@@ -1104,7 +1103,6 @@ attn_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     }
     tc_fence_before();
     __syncthreads();
-    if constexpr (CL > 1) cluster_sync_all();          // the peer's barriers are initialised before anyone arrives on them
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
     const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320,
@@ -1204,11 +1202,6 @@ attn_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         const int q = warp & 3;
         const int r = q * 32 + lane;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-        const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
-        // peer-side addresses of this thread's slots in the receive buffers and of the two remote barriers
-        const uint32_t peer_rx = CL > 1 ? mapa_cluster(smem_u32(sRX) + (uint32_t)r * 16u, crank ^ 1u) : 0u;
-        const uint32_t peer_full = CL > 1 ? mapa_cluster(smem_u32(rx_full), crank ^ 1u) : 0u;
-        const uint32_t peer_credit = CL > 1 ? mapa_cluster(smem_u32(tx_credit), crank ^ 1u) : 0u;
         for (int i = 0; i < nq; ++i) {
             const int b = i & 1;
             const int qi = (i + rot) % nq;
@@ -1227,7 +1220,7 @@ attn_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
                 // the previous tile's bulk reduction has finished READING the staging buffer
                 if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                float4* stg = reinterpret_cast<float4*>(sRX) + r;
+                float4* stg = reinterpret_cast<float4*>(sSTG) + r;
 #pragma unroll
                 for (int v = 0; v < 8; ++v)
                     stg[v * 128] = make_float4(0.125f * __uint_as_float(v0[4 * v]), 0.125f * __uint_as_float(v0[4 * v + 1]),
@@ -1241,39 +1234,10 @@ attn_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
                 if (issuer && !(ABL & 4)) {
                     float* tile = p.dq_acc + (((long long)n * p.heads + h) * nq + qi) * (AT_TQ * AT_D);
                     asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(tile),
-                                 "r"(smem_u32(sRX)), "r"(AT_TQ * AT_D * 4)
+                                 "r"(smem_u32(sSTG)), "r"(AT_TQ * AT_D * 4)
                                  : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
-                continue;
-            }
-            if constexpr (CL > 1) {
-                // columns [32 crank, +32) stay here, the other 32 go to the peer
-                float mine[32], theirs[32];
-#pragma unroll
-                for (int e = 0; e < 32; ++e) {         // selects, not array references: everything stays in registers
-                    mine[e] = __uint_as_float(crank ? v1[e] : v0[e]);
-                    theirs[e] = __uint_as_float(crank ? v0[e] : v1[e]);
-                }
-                if (i >= 2) mbar_wait_cluster(smem_u32(&tx_credit[b]), ((i >> 1) - 1) & 1);   // the peer has read tile i-2
-#pragma unroll
-                for (int v = 0; v < 8; ++v)
-                    st_cluster_v4(peer_rx + (uint32_t)(b * AB3_RX_BYTES + v * 2048), theirs[4 * v], theirs[4 * v + 1],
-                                  theirs[4 * v + 2], theirs[4 * v + 3]);
-                mbar_arrive_cluster(peer_full + (uint32_t)b * 8u);
-                mbar_wait_cluster(smem_u32(&rx_full[b]), (i >> 1) & 1);
-                const float4* rx = reinterpret_cast<const float4*>(sRX + b * AB3_RX_BYTES + r * 16);
-                float* dstc = dst + 32 * (int)crank;
-#pragma unroll
-                for (int v = 0; v < 8; ++v) {
-                    const float4 o = rx[v * 128];
-                    if (!(ABL & 4))
-                        red_add_v4(dstc + 4 * v, 0.125f * (mine[4 * v] + o.x), 0.125f * (mine[4 * v + 1] + o.y),
-                                   0.125f * (mine[4 * v + 2] + o.z), 0.125f * (mine[4 * v + 3] + o.w));
-                    else if (o.x + mine[4 * v] == 1.2345e-30f)
-                        red_add_v4(dstc, 0.f, 0.f, 0.f, 0.f);
-                }
-                mbar_arrive_cluster(peer_credit + (uint32_t)b * 8u);
                 continue;
             }
             if (ABL & 4) {      // ablation: no reductions
@@ -1418,7 +1382,6 @@ attn_bwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         }
     }
 
-    if constexpr (CL > 1) cluster_sync_all();          // no CTA leaves while its peer may still write to it
     tc_fence_before();
     __syncthreads();
     if (warp == 2) {
@@ -1546,19 +1509,20 @@ int attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const 
     p.lse = lse; p.delta = delta; p.dq_acc = dq_acc;
     p.dqkv = (__nv_bfloat16*)dqkv;
     dim3 grid(T / AT_TK, N * heads);
-    // PU_ATTN_BWD (A/B runs; measured at T = 4096, heads = 4, batch 64): default = attn_bwd_tc2_kernel<0>, 4.60 - 4.75 ms;
-    // 4 = sixteen softmax warps (each key half on its own warpgroups, setmaxnreg): 5.15 ms -- more warps do not help, the
-    // iteration is a chain of MMA <-> softmax hand-offs (commit, mbarrier wake-up, tcgen05.ld, STS + fence, arrive), not a
-    // throughput limit;
-    // 24 = every 4th exponential on the FMA pipe, 4.72 ms (every 2nd: 4.85 ms, removed); 3 = transposed scores
-    // (attn_bwd_tc3_kernel), 5.00 ms: half the shared-memory traffic but 56 instead of 42 MIO-queue instructions (MUFU,
-    // LDS, STS, LDTM / STTM) per thread and half-tile, and that queue is what the softmax warps stall on
+    // PU_ATTN_BWD (A/B runs; ms at T = 4096, heads = 4, batch 64).  Default 33 = attn_bwd_tc3_kernel<0, 1>: transposed scores
+    // and ONE TMA bulk reduction per dQ tile, 3.45 ms.  What the ablation runs (scripts/ablate_attn.py, profiles/
+    // r2_attention_ablation.md) showed: the per-lane red.global.add.v4 of the dQ partials cost 1.4 ms of the 4.61 ms of
+    // variant 20 and 1.95 ms of the 5.00 ms of variant 3 -- they queue in the LSU / MIO path that the softmax warps' STS and
+    // MUFU instructions share, which is why every earlier attempt (a dedicated drain warpgroup, 16 softmax warps = variant
+    // 4: 5.15 ms, exponentials on the FMA pipe = 24: 4.72 ms, transposed scores alone = 3: 5.00 ms) changed nothing.
+    // 20 = attn_bwd_tc2_kernel<0>: scores [q][k], P / dS through shared memory, per-lane reductions (round 1), 4.61 ms.
+    // 2xx / 3xx = ablations of 20 / 3 (wrong results on purpose): bit 1 no STS (2xx) / no LDS of lse, delta (3xx), bit 4 no
+    // dQ reductions, bit 8 no softmax work; 334 = 33 without issuing the bulk reductions.
     static const int variant = getenv("PU_ATTN_BWD") ? atoi(getenv("PU_ATTN_BWD")) : 33;
-    // the fused qkv bias gradient (column sums of dqkv) is produced by attn_bwd_tc2_kernel's epilogue and the dQ convert
-    // kernel; the transposed-score variant leaves it to the caller's separate pass
-    // the transposed-score kernel collects per-CTA partial sums in the tail of the dQ workspace (no atomics); its
-    // non-default launch forms (3, 32) leave the bias gradient to the caller's separate pass
-    const bool tc3 = variant == 3 || (variant >= 30 && variant < 40) || variant >= 300;
+    // qkv bias gradient (column sums of dqkv): variant 33 collects per-CTA partial sums in the tail of the dQ workspace
+    // (no atomics) and adds them up in attn_dbias_finish_kernel; the attn_bwd_tc2_kernel forms use atomics in their
+    // epilogue and in the dQ convert kernel; variant 3 leaves it to the caller's separate pass
+    const bool tc3 = variant == 3 || variant == 33 || variant >= 300;
     const bool part_bias = dbias != nullptr && (variant == 33 || variant == 334);
     const bool fuse_bias = dbias != nullptr && C <= 2048 && (!tc3 || part_bias);
     p.dbias = (fuse_bias && !part_bias) ? dbias : nullptr;
@@ -1585,16 +1549,16 @@ int attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const 
         PU_SMEM_ATTR(attn_bwd_tc3_kernel<A>, AB3_SMEM);                            \
         attn_bwd_tc3_kernel<A><<<grid, AB2_THREADS, AB3_SMEM, st>>>(tm, tmdo, p);   \
     }
-    PU_ABL2(201, 1) PU_ABL2(202, 2) PU_ABL2(204, 4) PU_ABL2(208, 8) PU_ABL2(212, 12) PU_ABL2(205, 5)
-    PU_ABL3(301, 1) PU_ABL3(303, 3) PU_ABL3(304, 4) PU_ABL3(305, 5) PU_ABL3(307, 7) PU_ABL3(308, 8) PU_ABL3(312, 12)
+    PU_ABL2(201, 1) PU_ABL2(204, 4) PU_ABL2(208, 8) PU_ABL2(212, 12)
+    PU_ABL3(301, 1) PU_ABL3(304, 4) PU_ABL3(305, 5) PU_ABL3(308, 8) PU_ABL3(312, 12)
     else if (variant == 33 || variant == 334) {
         // dQ partials as one TMA bulk reduction per tile; tile-major workspace
         if (variant == 33) {
-            PU_SMEM_ATTR((attn_bwd_tc3_kernel<0, 1, 1>), AB3_SMEM_CL);
-            attn_bwd_tc3_kernel<0, 1, 1><<<grid, AB2_THREADS, AB3_SMEM_CL, st>>>(tm, tmdo, p);
+            PU_SMEM_ATTR((attn_bwd_tc3_kernel<0, 1>), AB3_SMEM_BULK);
+            attn_bwd_tc3_kernel<0, 1><<<grid, AB2_THREADS, AB3_SMEM_BULK, st>>>(tm, tmdo, p);
         } else {
-            PU_SMEM_ATTR((attn_bwd_tc3_kernel<4, 1, 1>), AB3_SMEM_CL);
-            attn_bwd_tc3_kernel<4, 1, 1><<<grid, AB2_THREADS, AB3_SMEM_CL, st>>>(tm, tmdo, p);
+            PU_SMEM_ATTR((attn_bwd_tc3_kernel<4, 1>), AB3_SMEM_BULK);
+            attn_bwd_tc3_kernel<4, 1><<<grid, AB2_THREADS, AB3_SMEM_BULK, st>>>(tm, tmdo, p);
         }
         rc = check_launch("attn_bwd_tc3_bulk");
         if (rc) return rc;
@@ -1605,25 +1569,7 @@ int attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const 
         attn_dbias_finish_kernel<<<heads, 192, 0, st>>>(p.dbias_part, dbias, N, T / AT_TQ, heads, C);
         return check_launch("attn_dbias_finish");
     }
-    else if ((variant == 32 || variant == 324) && (T / AT_TK) % 2 == 0) {
-        // cluster pairs: adjacent key tiles of one (sample, head) exchange their dQ halves through distributed shared memory
-        auto kern = variant == 32 ? attn_bwd_tc3_kernel<0, 2> : attn_bwd_tc3_kernel<4, 2>;
-        if (variant == 32) PU_SMEM_ATTR((attn_bwd_tc3_kernel<0, 2>), AB3_SMEM_CL);
-        else PU_SMEM_ATTR((attn_bwd_tc3_kernel<4, 2>), AB3_SMEM_CL);
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = grid;
-        cfg.blockDim = dim3(AB2_THREADS);
-        cfg.dynamicSmemBytes = AB3_SMEM_CL;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        PU_CUDA(cudaLaunchKernelEx(&cfg, kern, tm, tmdo, p));
-    } else {
+    else {
         PU_SMEM_ATTR(attn_bwd_tc3_kernel<0>, AB3_SMEM);
         attn_bwd_tc3_kernel<0><<<grid, AB2_THREADS, AB3_SMEM, st>>>(tm, tmdo, p);
     }

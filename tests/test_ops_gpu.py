@@ -564,12 +564,12 @@ print('WORST', worst)
 """
 
 
-@pytest.mark.parametrize('variant', ['24', '3', '32', '33', '4', '20'])
+@pytest.mark.parametrize('variant', ['24', '3', '33', '4', '20'])
 def test_attention_bwd_variants(variant):
     """The attention-backward kernels that are not the default (PU_ATTN_BWD: 24 = every 4th exponential on the FMA pipe,
-    3 = transposed scores with P^T / dS^T as tensor-memory operands, 32 = the same in thread-block cluster pairs that add
-    their dQ partials through distributed shared memory) against autograd, one interpreter each (the switch is read once
-    per process)."""
+    3 = transposed scores with P^T / dS^T as tensor-memory operands and per-lane reductions, 20 = the round-1 layout; the
+    default, 33, is 3 with one TMA bulk reduction per dQ tile) against autograd, one interpreter each (the switch is read
+    once per process)."""
     import os
     import subprocess
     import sys
