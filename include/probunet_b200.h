@@ -214,6 +214,11 @@ int pu_attention_bwd(const void* qkv, const void* out, const void* dout, const f
 /* ---------------- prior / posterior encoders (prob_unet.py:32-36,60-72) ---------------- */
 /* y[N,2H,2W,C] = nearest-neighbour x2 of x (skip branch of the "up" blocks, networks.py:82-83,156) */
 int pu_upsample2(const void* x, void* y, int N, int H, int W, int C, int dtype, void* stream);
+/* transpose of the 2x resampling between a block's first GroupNorm(+SiLU) and its conv0 (networks.py:82-87, 164-166):
+ * g [N,H,W,C] = gradient wrt the pre-resample activation from dy wrt the resampled one.  resample = PU_RS_UP: dy is
+ * [N,2H,2W,C], g = sum of the four children; PU_RS_DOWN: dy is [N,H/2,W/2,C], g = 0.25 * dy[parent].  Lets pu_gn_bwd run
+ * its streaming (resample = PU_RS_NONE) kernels for the up / down blocks. */
+int pu_resample_grad(const void* dy, void* g, int N, int H, int W, int C, int resample, int dtype, void* stream);
 /* y[N,H/2,W/2,C] = 2x2 mean of x */
 int pu_avgpool2(const void* x, void* y, int N, int H, int W, int C, int dtype, void* stream);
 /* dr = 0.25 * dp[parent] * (r > 0)   (backward of AvgPool2d(ReLU(.))) */

@@ -1479,18 +1479,18 @@ attn_dq_convert_tiles_kernel(const float* __restrict__ acc, __nv_bfloat16* __res
     }
 }
 
-// dbias[part*C + h*64 + d] = sum over samples and tiles of the per-CTA partial sums ws[(n*heads + h)][tile][part*64 + d]
+// dbias[part*C + h*64 + d] += sum over samples and tiles of the per-CTA partial sums ws[(n*heads + h)][tile][part*64 + d]:
+// block (h, slice) adds up every gridDim.y-th (sample, tile) slot and issues one atomic per column (dbias zeroed by the
+// caller; a few dozen atomics per address instead of the thousands of the per-warp scheme)
 __global__ void __launch_bounds__(192)
 attn_dbias_finish_kernel(const float* __restrict__ ws, float* __restrict__ dbias, int N, int tiles, int heads, int C) {
     const int h = blockIdx.x, c = threadIdx.x;
     float tot = 0.f;
-    for (int n = 0; n < N; ++n) {
-        const float* base = ws + ((long long)(n * heads + h) * tiles) * 192 + c;
-        float part = 0.f;
-        for (int t = 0; t < tiles; ++t) part += base[(long long)t * 192];
-        tot += part;
+    for (int it = blockIdx.y; it < N * tiles; it += gridDim.y) {
+        const int n = it / tiles, t = it % tiles;
+        tot += ws[((long long)(n * heads + h) * tiles + t) * 192 + c];
     }
-    dbias[(c >> 6) * C + h * AT_D + (c & 63)] = tot;
+    atomicAdd(dbias + (c >> 6) * C + h * AT_D + (c & 63), tot);
 }
 
 bool attention_bwd_tc_applicable(int N, int T, int heads, int dtype) { return attention_tc_applicable(N, T, heads, dtype); }
@@ -1527,7 +1527,7 @@ int attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const 
     const bool fuse_bias = dbias != nullptr && C <= 2048 && (!tc3 || part_bias);
     p.dbias = (fuse_bias && !part_bias) ? dbias : nullptr;
     p.dbias_part = part_bias ? dq_acc + (size_t)N * T * C : nullptr;
-    if (p.dbias) PU_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * 3 * C, st));
+    if (p.dbias || part_bias) PU_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * 3 * C, st));
     if (dbias_done) *dbias_done = fuse_bias;
     if (variant == 20) {
         PU_SMEM_ATTR(attn_bwd_tc2_kernel<0>, AB2_SMEM);
@@ -1566,7 +1566,9 @@ int attention_bwd_tc(const void* qkv, const void* dout, const float* lse, const 
                                                                                    p.dbias_part);
         rc = check_launch("attn_dq_convert_tiles");
         if (rc || !part_bias) return rc;
-        attn_dbias_finish_kernel<<<heads, 192, 0, st>>>(p.dbias_part, dbias, N, T / AT_TQ, heads, C);
+        int slices = N * (T / AT_TQ) / 8;
+        slices = slices < 1 ? 1 : (slices > 64 ? 64 : slices);
+        attn_dbias_finish_kernel<<<dim3(heads, slices), 192, 0, st>>>(p.dbias_part, dbias, N, T / AT_TQ, heads, C);
         return check_launch("attn_dbias_finish");
     }
     else {

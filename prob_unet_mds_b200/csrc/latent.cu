@@ -56,6 +56,43 @@ __global__ void upsample2_kernel(const T* __restrict__ x, T* __restrict__ y, int
     }
 }
 
+// transpose of the 2x resampling that sits between a GroupNorm(+SiLU) and the conv it feeds (networks.py:82-87): the
+// gradient wrt the PRE-resample activation [N,H,W,C] from the gradient dy wrt the resampled one.
+//   UP   (forward = nearest x2, dy is [N,2H,2W,C]):   g[y][x] = sum of the four children of dy
+//   DOWN (forward = 2x2 mean,  dy is [N,H/2,W/2,C]):  g[y][x] = 0.25 * dy[y/2][x/2]
+template <typename T, bool UP>
+__global__ void resample_grad_kernel(const T* __restrict__ dy, T* __restrict__ g, int N, int H, int W, int C) {
+    const int nvec = C / 8;
+    const long long total = (long long)N * H * W * nvec;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i % nvec);
+        long long t = i / nvec;
+        const int x = (int)(t % W);
+        t /= W;
+        const int y = (int)(t % H);
+        const int n = (int)(t / H);
+        float o[8];
+        if (UP) {
+            const int OH = 2 * H, OW = 2 * W;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {       // same order as the gather it replaces (gn_gather8): bit-identical in fp32
+                float a[8];
+                ld8(dy + (((long long)n * OH + 2 * y + (k >> 1)) * OW + 2 * x + (k & 1)) * C + v * 8, a);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] += a[e];
+            }
+        } else {
+            const int OH = H / 2, OW = W / 2;
+            ld8(dy + (((long long)n * OH + (y >> 1)) * OW + (x >> 1)) * C + v * 8, o);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] *= 0.25f;
+        }
+        st8(g + (((long long)n * H + y) * W + x) * C + v * 8, o);
+    }
+}
+
 // dr[n,y,x,c] = scale * dp[n,y/2,x/2,c] * (r > 0)
 template <typename T>
 __global__ void relu_pool_bwd_kernel(const T* __restrict__ dp, const T* __restrict__ r, T* __restrict__ dr, int N, int H,
@@ -412,6 +449,25 @@ int pu_loss_bwd_scales(const float* g_total, const float* g_recon, const float* 
     PU_REQUIRE(out2, "pu_loss_bwd_scales: bad arguments");
     loss_bwd_scales_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(g_total, g_recon, g_kl, beta, out2);
     return check_launch("loss_bwd_scales");
+}
+
+int pu_resample_grad(const void* dy, void* g, int N, int H, int W, int C, int resample, int dtype, void* stream) {
+    PU_REQUIRE(dy && g && N > 0 && H > 0 && W > 0 && C % 8 == 0, "pu_resample_grad: bad arguments");
+    PU_REQUIRE(resample == PU_RS_UP || (resample == PU_RS_DOWN && H % 2 == 0 && W % 2 == 0),
+               "pu_resample_grad: resample must be PU_RS_UP or PU_RS_DOWN (even H, W); got %d, %dx%d", resample, H, W);
+    PU_REQUIRE(dtype == PU_F32 || dtype == PU_BF16, "pu_resample_grad: bad dtype");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long total = (long long)N * H * W * (C / 8);
+    const bool up = resample == PU_RS_UP;
+    if (dtype == PU_F32) {
+        if (up) resample_grad_kernel<float, true><<<grid_for(total), 256, 0, st>>>((const float*)dy, (float*)g, N, H, W, C);
+        else resample_grad_kernel<float, false><<<grid_for(total), 256, 0, st>>>((const float*)dy, (float*)g, N, H, W, C);
+    } else {
+        using B = __nv_bfloat16;
+        if (up) resample_grad_kernel<B, true><<<grid_for(total), 256, 0, st>>>((const B*)dy, (B*)g, N, H, W, C);
+        else resample_grad_kernel<B, false><<<grid_for(total), 256, 0, st>>>((const B*)dy, (B*)g, N, H, W, C);
+    }
+    return check_launch("resample_grad");
 }
 
 int pu_upsample2(const void* x, void* y, int N, int H, int W, int C, int dtype, void* stream) {

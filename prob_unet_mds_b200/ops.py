@@ -300,6 +300,16 @@ def upsample2(x):
     return y
 
 
+def resample_grad(dy, resample):
+    """Gradient wrt the pre-resample activation (see pu_resample_grad): dy is NHWC at the resampled resolution."""
+    N, OH, OW, Cc = _nhwc(dy)
+    H, W = (OH // 2, OW // 2) if resample == L.RS_UP else (OH * 2, OW * 2)
+    g = torch.empty((N, H, W, Cc), dtype=dy.dtype, device=dy.device)
+    check(lib().pu_resample_grad(ptr(dy), ptr(g), N, H, W, Cc, resample, dtype_code(dy.dtype), stream_ptr()),
+          'resample_grad')
+    return g
+
+
 def avgpool2(x):
     N, H, W, Cc = _nhwc(x)
     y = torch.empty((N, H // 2, W // 2, Cc), dtype=x.dtype, device=x.device)

@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 CMD="python scripts/heavy_kernels.py"
 $CMD > gpurun_out/plain_heavy.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain_heavy.log; exit 1; }
 ncu --set full --clock-control none \
-    -k regex:'conv_tc_kernel|wgrad_tc|attn_fwd_tc|attn_bwd_tc|gn_bwd_apply|gn_bwd_reduce|gn_apply_kernel|gn_stats_kernel|fcomb_members|pack_weights_multi|adamw_multi' \
+    -k regex:'conv_tc_kernel|wgrad_tc|attn_fwd_tc|attn_bwd_tc|attn_dq_convert|gn_bwd_apply|gn_bwd_reduce|gn_apply_kernel|gn_stats_kernel|fcomb_members|pack_weights_multi|adamw_multi' \
     -f -o /tmp/prof_r2_heavy $CMD > gpurun_out/ncu_heavy.log 2>&1
 echo "capture exit=$?"
 ncu -i /tmp/prof_r2_heavy.ncu-rep --page raw --csv > gpurun_out/r2_heavy_raw.csv 2>gpurun_out/ncu_export.log

@@ -612,6 +612,27 @@ def test_attention_tc_score_jumps():
     assert max_err(lse, lse_ref) < 2e-3 * lse_ref.abs().max().item()
 
 
+@pytest.mark.parametrize('dtype', ['f32', 'bf16'])
+def test_resample_grad(dtype):
+    """pu_resample_grad = transpose of the nearest-x2 / 2x2-mean resampling (networks.py:82-87 with the [1,1] filter)."""
+    dt = torch.float32 if dtype == 'f32' else torch.bfloat16
+    N, H, W, Cc = 2, 6, 10, 16
+    x = rnd(N, Cc, H, W, seed=3).requires_grad_(True)
+    up = torch.nn.functional.interpolate(x, scale_factor=2, mode='nearest')
+    dy = rnd(N, Cc, 2 * H, 2 * W, seed=4).to(dt).float()
+    up.backward(dy)
+    g = ops.resample_grad(dy.permute(0, 2, 3, 1).contiguous().to(dt), L.RS_UP)
+    assert g.shape == (N, H, W, Cc)
+    assert rel_err(g.permute(0, 3, 1, 2), x.grad) < (1e-6 if dtype == 'f32' else 4e-3)
+    x2 = rnd(N, Cc, H, W, seed=5).requires_grad_(True)
+    down = torch.nn.functional.avg_pool2d(x2, 2)
+    dy2 = rnd(N, Cc, H // 2, W // 2, seed=6).to(dt).float()
+    down.backward(dy2)
+    g2 = ops.resample_grad(dy2.permute(0, 2, 3, 1).contiguous().to(dt), L.RS_DOWN)
+    assert g2.shape == (N, H, W, Cc)
+    assert rel_err(g2.permute(0, 3, 1, 2), x2.grad) < 1e-6        # a power-of-two scale: exact in bf16 too
+
+
 def test_encoder_glue():
     x = rnd(2, 64, 8, 8, seed=1)
     xs = nhwc(x, torch.float32)
