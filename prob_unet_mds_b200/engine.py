@@ -172,10 +172,10 @@ class UNetEngine:
         # activation tensor to them for its consumers (the next block's norm0, also across a skip concatenation)
         self._q = {}
         self._prod = {}       # id(activation) -> bias parameter of the conv that produced it (training tape only)
-        # (quads need group sizes that are multiples of 4: model_channels % 128 == 0 -- true for the Probabilistic U-Net's
-        # backbone, not for the 64-channel deterministic baseline, whose 192-channel levels have groups of 6)
-        self._fused_stats = (os.environ.get('PROBUNET_B200_FUSED_GN_STATS', '1') != '0'
-                             and u.model_channels % 128 == 0)
+        # (a consumer can use the quads when its groups are made of whole quads -- _stats decides per tensor: always true for
+        # the Probabilistic U-Net's 128-channel backbone; in the 64-channel deterministic baseline the 192-, 320- and
+        # 448-channel norms have groups of 6, 10 and 14 channels and take the separate statistics pass)
+        self._fused_stats = os.environ.get('PROBUNET_B200_FUSED_GN_STATS', '1') != '0'
         self.cache.refresh()
         for name, mod in u.enc.items():
             if isinstance(mod, torch.nn.Module) and hasattr(mod, 'norm0'):
@@ -214,7 +214,12 @@ class UNetEngine:
 
     def _conv_q(self, *args, **kw):
         """conv2d whose output feeds a GroupNorm: its epilogue also emits the per-quad (sum, sumsq)."""
-        if not self._fused_stats:
+        src, k = args[0], args[3]
+        cin = src.shape[3] + (kw['src1'].shape[3] if kw.get('src1') is not None else 0)
+        # the statistics epilogue hides behind the tile's MMAs from K = 9 x 128 on; the 64-channel 3x3 convs of the
+        # deterministic baseline are epilogue-bound with it (+1.5 ms per step at 256x256, what the separate pass costs)
+        hidden = k == 1 or k * k * cin >= 1152 or self.dtype != torch.bfloat16
+        if not self._fused_stats or not hidden:
             return ops.conv2d(*args, **kw)
         y, q = ops.conv2d(*args, want_qstats=True, **kw)
         self._q[id(y)] = (weakref.ref(y), q)     # weak: the table must not keep activations alive in eval mode
@@ -226,7 +231,9 @@ class UNetEngine:
 
     def _stats(self, xa, xb=None):
         qa, qb = self._quads(xa), self._quads(xb)
-        if qa is None or (xb is not None and qb is None):
+        C = xa.shape[3] + (xb.shape[3] if xb is not None else 0)
+        whole_quads = (C // ops.gn_groups(C)) % 4 == 0 and xa.shape[3] % 4 == 0
+        if qa is None or (xb is not None and qb is None) or not whole_quads:
             return ops.gn_stats(xa, xb)
         return ops.gn_stats_from_quads(qa, qb)
 
