@@ -135,6 +135,31 @@ int make_mat_tmap(CUtensorMap* m, const void* ptr, long long rows, long long col
     return PU_OK;
 }
 
+// fp32 packed weight gradient [rows = Cout][cols = taps * (C0 + C1)] -> 2-D map, box {32 floats = 128 B, 128 rows}, 128B
+// swizzle: the destination of the weight-gradient kernel's cp.reduce.async.bulk.tensor epilogue
+int make_dw_tmap(CUtensorMap* m, const void* ptr, long long rows, long long cols) {
+    const TmapKey key{ptr, rows, (cols << 12) | 0x7f1LL};
+    if (tmap_lookup(key, m)) return PU_OK;
+    EncodeTiledFn enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled entry point not available");
+        return PU_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+    cuuint32_t box[2] = {32, 128};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(weight gradient %lld x %lld) failed: %d", rows, cols, (int)r);
+        return PU_ERR_CUDA;
+    }
+    tmap_store(key, *m);
+    return PU_OK;
+}
+
 static int num_sms() {
     static int n = 0;
     if (!n) {
@@ -855,7 +880,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
 constexpr int WG_HALO_W = WG_TW + 2;
 constexpr int WG_HALO = WG_HALO_W * WG_TH * 128;     // one [18 x 4 px][64 ch] halo sub-tile = 9216 B (9 swizzle atoms)
 
-template <int BN, int MODE>
+template <int BN, int MODE, bool TRED = false>
 struct Wgrad2Cfg {
     static_assert(MODE != 3 || BN <= 128, "MODE 3 keeps three accumulators of BN columns in 512 TMEM columns");
     static constexpr int NACC = (MODE == 3) ? 3 : 2;
@@ -864,16 +889,20 @@ struct Wgrad2Cfg {
     static constexpr int B_SUBS = ((MODE == 1) ? 1 : 2) * (BN / 64);
     static constexpr int B_BYTES = (MODE == 3) ? (BN / 64) * WG_HALO : B_SUBS * WG_SUB;
     static constexpr int STAGE_BYTES = A_SUBS * WG_SUB + B_BYTES;
-    static constexpr int MAX_STAGES = (227 * 1024 - 1280) / STAGE_BYTES;
+    // TRED: the epilogue stages 32-column chunks of the accumulators in two 16 KB shared-memory tiles and hands them to
+    // the TMA engine (cp.reduce.async.bulk.tensor add.f32) instead of issuing per-lane red.global.add.v4
+    static constexpr int STG_BYTES = TRED ? 2 * 128 * 128 : 0;
+    static constexpr int MAX_STAGES = (227 * 1024 - 1280 - STG_BYTES - (TRED ? 1024 : 0)) / STAGE_BYTES;
     static constexpr int STAGES = MAX_STAGES > 6 ? 6 : MAX_STAGES;
-    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256 + STG_BYTES + (TRED ? 1024 : 0);
 };
 
-template <int BN, int MODE>
+template <int BN, int MODE, bool TRED = false>
 __global__ void __launch_bounds__(256, 1)
 wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX0,
-                 const __grid_constant__ CUtensorMap tmX1, const WgradTcParams p) {
-    using Cfg = Wgrad2Cfg<BN, MODE>;
+                 const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmDW,
+                 const WgradTcParams p) {
+    using Cfg = Wgrad2Cfg<BN, MODE, TRED>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
     constexpr int A_BYTES2 = Cfg::A_SUBS * WG_SUB;
@@ -887,6 +916,8 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant
     uint64_t* tfull = bars + 2 * STAGES;
     uint64_t* tempty = tfull + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
+    // TRED: two 1024-aligned [128 rows][128 B] staging tiles behind the barrier block
+    uint8_t* stg = smem + ((STAGES * STAGE_BYTES + 256 + 1023) & ~1023);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -895,6 +926,7 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant
         prefetch_tmap(&tmDY);
         prefetch_tmap(&tmX0);
         prefetch_tmap(&tmX1);
+        if (TRED) prefetch_tmap(&tmDW);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -1046,6 +1078,7 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant
         const int q = warp - 4;
         const long long row_stride = (long long)p.taps * Ctot;
         uint32_t it = 0;
+        uint32_t chunk_no = 0;          // TRED: chunks staged so far by this CTA (staging tile = chunk_no & 1)
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
             int split, tg, cg, ci_t;
             decode(item, split, tg, cg, ci_t);
@@ -1053,6 +1086,46 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant
             const int ntap = (MODE == 3) ? 3 : (MODE == 2 && tap0 + 1 < p.taps) ? 2 : 1;
             mbar_wait(smem_u32(tfull), it & 1);
             tc_fence_after();
+            if constexpr (TRED) {
+                // (MODE 3 only) every 128 x 32 fp32 chunk of the three accumulators: TMEM -> registers -> swizzled staging
+                // tile -> ONE cp.reduce.async.bulk.tensor (add.f32) into the packed gradient.  The tensor memory is
+                // released as soon as the last chunk has been read, the reductions drain behind the next item's MMAs.
+                const bool issuer = (warp == 4 && lane == 0);
+                const int row = q * 32 + lane;
+                constexpr int NCH = 3 * (BN / 32);
+#pragma unroll 1
+                for (int ch = 0; ch < NCH; ++ch, ++chunk_no) {
+                    const int half = ch / (BN / 32), c = (ch % (BN / 32)) * 32;
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + half * Cfg::ACC_STRIDE + c, v);
+                    // the reduction issued two chunks ago has finished READING its staging tile
+                    if (issuer && chunk_no >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    tc_wait_ld();
+                    if (ch == NCH - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(tempty));
+                    }
+                    uint8_t* tile = stg + (chunk_no & 1u) * (128 * 128);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)     // 128B swizzle: 16-byte chunk j of row r lives at chunk j ^ (r & 7)
+                        *reinterpret_cast<uint4*>(tile + row * 128 + ((j ^ (row & 7)) << 4)) =
+                            make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    fence_proxy_async();
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (issuer) {
+                        const int col = (tap0 + half) * Ctot + ci_t * BN + c;
+                        asm volatile(
+                            "cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                                reinterpret_cast<uint64_t>(&tmDW)),
+                            "r"(col), "r"(cg * 128), "r"(smem_u32(tile))
+                            : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+                continue;
+            }
 #pragma unroll 1
             for (int half = 0; half < Cfg::NACC; ++half) {
                 int co, tap;
@@ -1086,6 +1159,7 @@ wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(tempty));
         }
+        if (TRED && warp == 4 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 
     tc_fence_before();
@@ -1216,7 +1290,11 @@ static int wgrad_tc_launch_bn(const PuWgradArgs* a, cudaStream_t st) {
     const double t_mma = NACC * 2.0 * BN;                        // 4 x (128 x BN x 16) MMAs per accumulator and block
     const double t_feed = op_bytes / 48.0;                       // measured L2 -> shared-memory rate, B/clk/SM
     const double t_blk = t_mma > t_feed ? t_mma : t_feed;
-    const double t_epi = NACC * 128.0 * BN * 4.0 / 21.0 + 2000.0;   // measured L2 reduction rate, B/clk/SM
+    static const bool tred_on = !(getenv("PU_WGRAD_TRED") && getenv("PU_WGRAD_TRED")[0] == '0');   // A/B switch
+    const bool tred = MODE == 3 && tred_on;
+    // per-lane reductions drain at the L2 reduction rate (measured 21 B/clk/SM) with the tensor pipe idle; the TMA-reduce
+    // epilogue only has to stage the accumulators in shared memory
+    const double t_epi = tred ? NACC * 128.0 * BN * 4.0 / 64.0 + 2000.0 : NACC * 128.0 * BN * 4.0 / 21.0 + 2000.0;
     long long max_split = cdivll(p.px_blocks, 8);   // at least 8 K-blocks (512 pixels) per item
     if (max_split < 1) max_split = 1;
     const int sms = num_sms();
@@ -1256,10 +1334,23 @@ static int wgrad_tc_launch_bn(const PuWgradArgs* a, cudaStream_t st) {
         using Cfg = WgradTcCfg<BN>;
         PU_SMEM_ATTR(wgrad_tc_kernel<BN>, Cfg::SMEM);
         wgrad_tc_kernel<BN><<<grid, 256, Cfg::SMEM, st>>>(tDY, tX0, tX1, p);
+    } else if constexpr (MODE == 3) {
+        if (tred) {
+            CUtensorMap tDW;
+            rc = make_dw_tmap(&tDW, a->dw, a->Cout, (long long)p.taps * (a->C0 + a->C1));
+            if (rc) return rc;
+            using Cfg = Wgrad2Cfg<BN, 3, true>;
+            PU_SMEM_ATTR((wgrad_tc2_kernel<BN, 3, true>), Cfg::SMEM);
+            wgrad_tc2_kernel<BN, 3, true><<<grid, 256, Cfg::SMEM, st>>>(tDY, tX0, tX1, tDW, p);
+        } else {
+            using Cfg = Wgrad2Cfg<BN, 3, false>;
+            PU_SMEM_ATTR((wgrad_tc2_kernel<BN, 3, false>), Cfg::SMEM);
+            wgrad_tc2_kernel<BN, 3, false><<<grid, 256, Cfg::SMEM, st>>>(tDY, tX0, tX1, tX0, p);
+        }
     } else {
         using Cfg = Wgrad2Cfg<BN, MODE>;
         PU_SMEM_ATTR((wgrad_tc2_kernel<BN, MODE>), Cfg::SMEM);
-        wgrad_tc2_kernel<BN, MODE><<<grid, 256, Cfg::SMEM, st>>>(tDY, tX0, tX1, p);
+        wgrad_tc2_kernel<BN, MODE><<<grid, 256, Cfg::SMEM, st>>>(tDY, tX0, tX1, tX0, p);
     }
     return check_launch("wgrad_tc");
 }
