@@ -136,20 +136,24 @@ template <typename T>
 __global__ void __launch_bounds__(GN_THREADS)
 gn_stats_kernel(const T* __restrict__ s0, const T* __restrict__ s1, int C0, int C1, int HW, int G, int rows,
                 double* __restrict__ stats) {
-    extern __shared__ float sm[];   // [G][2]
+    // fp32 only inside one trip (four rows): the running sums per thread, per block and per sample are fp64.  (With fp32
+    // thread and block sums the statistics depended on the block partition at the 1e-6 level -- enough to move the loss
+    // by 1.3e-5 between a batch and its two halves, and the fp32-mode gradients by 5e-5.)
+    extern __shared__ double smd_stats[];   // [G][2]
+    double* sm = smd_stats;
     const int C = C0 + C1, nvec = C / 8, Cg = C / G;
     const int n = blockIdx.y;
     const int PL = GN_THREADS / nvec;
     const int v = threadIdx.x % nvec, pl = threadIdx.x / nvec;
-    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sm[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sm[i] = 0.0;
     __syncthreads();
     const int r0 = blockIdx.x * rows;
     int r1 = r0 + rows;
     if (r1 > HW) r1 = HW;
     if (pl < PL) {
-        float s[8], q[8];
+        double s[8], q[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+        for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.0;
         const int c0 = v * 8;
         const T* base = (c0 < C0) ? (s0 + (long long)n * HW * C0 + c0) : (s1 + (long long)n * HW * C1 + (c0 - C0));
         const int stride = (c0 < C0) ? C0 : C1;
@@ -167,6 +171,9 @@ gn_stats_kernel(const T* __restrict__ s0, const T* __restrict__ s1, int C0, int 
                 const int rr = r + (SNB + j) * PL;
                 if (rr < r1) nxt[j] = ldraw(base + (long long)rr * stride);
             }
+            float ts[8], tq[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ts[e] = tq[e] = 0.f;
 #pragma unroll
             for (int j = 0; j < SNB; ++j) {
                 if (r + j * PL >= r1) break;
@@ -174,16 +181,21 @@ gn_stats_kernel(const T* __restrict__ s0, const T* __restrict__ s1, int C0, int 
                 unpack(raw[j], x);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    s[e] += x[e];
-                    q[e] = fmaf(x[e], x[e], q[e]);
+                    ts[e] += x[e];
+                    tq[e] = fmaf(x[e], x[e], tq[e]);
                 }
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                s[e] += (double)ts[e];
+                q[e] += (double)tq[e];
             }
 #pragma unroll
             for (int j = 0; j < SNB; ++j) raw[j] = nxt[j];
         }
         // combine channels of the same group before touching shared memory
         int g = c0 / Cg;
-        float gs = 0.f, gq = 0.f;
+        double gs = 0.0, gq = 0.0;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int ge = (c0 + e) / Cg;
@@ -191,7 +203,7 @@ gn_stats_kernel(const T* __restrict__ s0, const T* __restrict__ s1, int C0, int 
                 atomicAdd(&sm[2 * g], gs);
                 atomicAdd(&sm[2 * g + 1], gq);
                 g = ge;
-                gs = gq = 0.f;
+                gs = gq = 0.0;
             }
             gs += s[e];
             gq += q[e];
@@ -200,7 +212,7 @@ gn_stats_kernel(const T* __restrict__ s0, const T* __restrict__ s1, int C0, int 
         atomicAdd(&sm[2 * g + 1], gq);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(stats + (long long)n * G * 2 + i, (double)sm[i]);
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(stats + (long long)n * G * 2 + i, sm[i]);
 }
 
 // ---- statistics per quad of channels (the layout conv_tc_kernel's epilogue produces), CUDA-core fallback ----
@@ -1186,7 +1198,7 @@ int pu_gn_stats(const void* src0, const void* src1, int C0, int C1, int N, int H
     const int PL = GN_THREADS / (C / 8);
     const int rows = rows_per_block(HW, N, PL * 8);
     dim3 grid(cdiv(HW, rows), N);
-    const size_t smem = sizeof(float) * 2 * G;
+    const size_t smem = sizeof(double) * 2 * G;
     if (dtype == PU_F32)
         gn_stats_kernel<float><<<grid, GN_THREADS, smem, st>>>((const float*)src0, (const float*)src1, C0, C1, HW, G, rows,
                                                                stats);
