@@ -292,9 +292,14 @@ class UNetEngine:
         GroupNorm kernels of the main stream.  backward() joins the streams before returning."""
         side = self._side_stream()
         if side is None:
-            dwp = ops.conv2d_wgrad(src0, dy, k, src1=src1)
             g = grads.alloc(param)          # a view into an all-reduce bucket under data parallelism
-            ops.unpack_wgrad(dwp, g, perm=perm)
+            cin = src0.shape[3] + (src1.shape[3] if src1 is not None else 0)
+            if k == 1 and perm is None and tuple(param.shape[:2]) == (dy.shape[3], cin):
+                # a 1x1 weight's packed layout [Cout][1][Cin] IS its OIHW layout: the kernel writes the gradient in place
+                ops.conv2d_wgrad(src0, dy, 1, src1=src1, dw=g.view(dy.shape[3], 1, 1, cin))
+            else:
+                dwp = ops.conv2d_wgrad(src0, dy, k, src1=src1)
+                ops.unpack_wgrad(dwp, g, perm=perm)
             grads[id(param)] = g            # "written": may trigger the bucket's all-reduce
             return
         main = torch.cuda.current_stream()
