@@ -1011,9 +1011,10 @@ attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward kernel, transposed scores (round 2).  ncu on attn_bwd_tc2_kernel (profiles/r2_ncu_attention.md): the eight
-// softmax warps spend 31 % of their time in MIO throttle on the STS.128 of P and dS, 19 % waiting for MUFU results
-// behind the same queue, and the tensor core pulls 224 KB of operands per (q tile, key tile) out of shared memory.
+// backward kernel, transposed scores (round 2; with BULK = 1 the default).  ncu on attn_bwd_tc2_kernel
+// (profiles/r2_ncu_attention_tc2_top_stalls.tsv): the eight softmax warps spend 31 % of their time in MIO throttle, 19 %
+// waiting for MUFU results behind the same queue, and the tensor core pulls 224 KB of operands per (q tile, key tile) out
+// of shared memory.  (What filled that queue were the drain warps' per-lane reductions: see BULK below.)
 // Here the CTA computes the TRANSPOSED tiles
 //     S^T = K_j Q_i^T ,  dP^T = V_j dO_i^T            (lanes = keys, columns = queries; two 64-query halves)
 // so that P^T and dS^T are born in the layout the dV / dK accumulations want as their A operand:
