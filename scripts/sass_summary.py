@@ -1,5 +1,6 @@
 """Opcode census of the shipped library (cuobjdump -sass): per kernel, the counts of the SASS mnemonics that prove which
-hardware paths it uses -- UTCHMMA (tcgen05.mma), UTMALDG (TMA tensor loads), UBLKCP (cp.async.bulk), LDTM / STTM
+hardware paths it uses -- UTCHMMA (tcgen05.mma), UTMALDG (TMA tensor loads), UTMAREDG (cp.reduce.async.bulk.tensor), UBLKCP (cp.async.bulk),
+UBLKRED (cp.reduce.async.bulk), LDTM / STTM
 (tcgen05.ld / st), UTCBAR (tcgen05.commit), SYNCS (mbarrier), FFMA2 (packed fp32), REDG / RED (global reductions).
 
     python scripts/sass_summary.py > profiles/r2_sass_summary.txt        (no GPU needed)"""
@@ -11,7 +12,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, 'prob_unet_mds_b200', 'libprobunet_b200.so')
-KEYS = ['UTCHMMA', 'UTMALDG', 'UBLKCP', 'LDTM', 'STTM', 'UTCBAR', 'SYNCS', 'FFMA2', 'REDG', 'MUFU', 'HMMA']
+KEYS = ['UTCHMMA', 'UTMALDG', 'UTMAREDG', 'UBLKCP', 'UBLKRED', 'LDTM', 'STTM', 'UTCBAR', 'SYNCS', 'FFMA2', 'REDG', 'MUFU', 'HMMA']
 
 out = subprocess.run(['cuobjdump', '-sass', LIB], capture_output=True, text=True, check=True).stdout
 counts = collections.OrderedDict()
