@@ -574,6 +574,292 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdPara
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// forward, two query tiles per CTA, O ACCUMULATED IN TENSOR MEMORY (the default; PU_ATTN_FWD=2 selects the kernel above).  attn_fwd_tc2_kernel reads O_j back
+// after every key tile and keeps the running output in 64 registers per thread (6 % of its time by ablation, and the
+// reason it has no registers left to prefetch S).  Here O = sum_j P_j V_j stays in TMEM for the whole key walk (PV MMAs
+// with the accumulate flag) and the softmax reference of a row only moves when the running maximum has drifted more than
+// 2^8 above it (P <= 256: harmless in bf16 / fp32): then -- rarely after the first few tiles -- the warp waits for the
+// pending PV MMA, rescales its 32 x 64 slice of O in place (tcgen05.ld / st) and its row sums.  The exact two-pass
+// fallback for scores more than 2^64 above the reference is kept.  With the registers that frees, the next 32-column
+// chunk of S is already in flight while the current one is exponentiated.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(384, 1)
+attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sQ = smem;                                        // q tile t at + t*TILE
+    uint8_t* sKV = sQ + 2 * AT_TILE;                           // stage s: K at +s*2*TILE, V at +s*2*TILE + TILE
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + A2_KV_STAGES * 2 * AT_TILE);
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;
+    uint64_t* kv_empty = kv_full + A2_KV_STAGES;
+    uint64_t* s_full = kv_empty + A2_KV_STAGES;    // [2] per q tile
+    uint64_t* s_empty = s_full + 2;
+    uint64_t* p_full = s_empty + 2;
+    uint64_t* o_full = p_full + 2;                 // PV_j of q tile t has completed (P_j consumed, O up to date)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nh = blockIdx.y, n = nh / p.heads, h = nh % p.heads;
+    const int q0 = blockIdx.x * 2 * AT_TQ;
+    const int ntiles = p.T / AT_TK;
+    const int row_base = n * p.T;
+    const int colQ = h * AT_D, colK = p.C + h * AT_D, colV = 2 * p.C + h * AT_D;
+
+    if (warp == 0 && lane == 0) prefetch_tmap(&tmQKV);
+    if (warp == 1 && lane == 0) {
+        mbar_init(smem_u32(q_full), 1);
+        for (int s = 0; s < A2_KV_STAGES; ++s) {
+            mbar_init(smem_u32(&kv_full[s]), 1);
+            mbar_init(smem_u32(&kv_empty[s]), 1);
+        }
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(smem_u32(&s_full[t]), 1);
+            mbar_init(smem_u32(&s_empty[t]), 4);
+            mbar_init(smem_u32(&p_full[t]), 4);
+            mbar_init(smem_u32(&o_full[t]), 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(smem_u32(tmem_slot), 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    const uint32_t tS = tmem_base;           // S[t] at + t*128
+    const uint32_t tO = tmem_base + 256;     // O[t] at + t*64
+    const uint32_t tP = tmem_base + 384;     // P[t] at + t*64 (bf16 pairs)
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(smem_u32(q_full), 2 * AT_TILE);
+            tma_load_2d(smem_u32(sQ), &tmQKV, smem_u32(q_full), colQ, row_base + q0);
+            tma_load_2d(smem_u32(sQ + AT_TILE), &tmQKV, smem_u32(q_full), colQ, row_base + q0 + AT_TQ);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int j = 0; j < ntiles; ++j) {
+                mbar_wait(smem_u32(&kv_empty[stage]), phase ^ 1);
+                const uint32_t fb = smem_u32(&kv_full[stage]);
+                mbar_expect_tx(fb, 2 * AT_TILE);
+                tma_load_2d(smem_u32(sKV + stage * 2 * AT_TILE), &tmQKV, fb, colK, row_base + j * AT_TK);
+                tma_load_2d(smem_u32(sKV + stage * 2 * AT_TILE + AT_TILE), &tmQKV, fb, colV, row_base + j * AT_TK);
+                if (++stage == A2_KV_STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t IDESC_S = idesc_bf16_f32(128, 128, 0, 0);
+        constexpr uint32_t IDESC_O = idesc_bf16_f32(128, 64, 0, 1);
+        mbar_wait(smem_u32(q_full), 0);
+        auto issue_s = [&](int t, uint32_t k_addr) {
+            const uint32_t q_addr = smem_u32(sQ + t * AT_TILE);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                mma_f16_ss(tS + t * 128, smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                           smem_desc_sw128(k_addr + k * 32, 16, 1024), IDESC_S, k ? 1u : 0u);
+            mma_commit(smem_u32(&s_full[t]));
+        };
+        int stage = 0;
+        uint32_t phase = 0;
+        mbar_wait(smem_u32(&kv_full[0]), 0);
+        tc_fence_after();
+        issue_s(0, smem_u32(sKV));
+        issue_s(1, smem_u32(sKV));
+        for (int j = 0; j < ntiles; ++j) {
+            const uint32_t jp = j & 1;
+            const uint32_t v_addr = smem_u32(sKV + stage * 2 * AT_TILE + AT_TILE);
+            int nstage = stage + 1;
+            uint32_t nphase = phase;
+            if (nstage == A2_KV_STAGES) {
+                nstage = 0;
+                nphase ^= 1;
+            }
+            const bool more = j + 1 < ntiles;
+            if (more) mbar_wait(smem_u32(&kv_full[nstage]), nphase);
+            for (int t = 0; t < 2; ++t) {
+                // P_j written (and O rescaled if the reference moved), S_j consumed: refill S, then O += P_j V_j
+                mbar_wait(smem_u32(&p_full[t]), jp);
+                mbar_wait(smem_u32(&s_empty[t]), jp);
+                tc_fence_after();
+                if (more) issue_s(t, smem_u32(sKV + nstage * 2 * AT_TILE));
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    mma_f16_ts(tO + t * 64, tP + t * 64 + k * 8, smem_desc_sw128(v_addr + k * 2048, 8192, 1024),
+                               IDESC_O, (j | k) ? 1u : 0u);
+                mma_commit(smem_u32(&o_full[t]));
+            }
+            mma_commit(smem_u32(&kv_empty[stage]));
+            stage = nstage;
+            phase = nphase;
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        const int t = (warp - 4) >> 2;                     // q tile of this warpgroup
+        const int r = q * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        const float sc = 0.125f * 1.4426950408889634f;
+        float m = -INFINITY, l = 0.f;      // running maximum (scaled, log2 domain) and row sum relative to m_ref
+        float m_ref = 0.f;                 // reference of O, l and of the P tiles written so far
+        float pend_ref = 0.f;              // reference to move to once the pending PV MMA has completed
+        bool pending = false;              // warp-uniform
+        // exponentials of one preloaded 32-column chunk: bf16 pairs into pk, row sum / row maximum updated
+        auto exp_chunk = [&](const uint32_t (&v)[32], float ref, float& rs, float& mxr, uint32_t (&pk)[16]) {
+            const float2 sc2 = make_float2(sc, sc), nref2 = make_float2(-ref, -ref);
+            float2 rs2 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const float2 s2 = make_float2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
+                mxr = fmaxf(fmaxf(s2.x, s2.y), mxr);
+                const float2 x2 = ffma2(s2, sc2, nref2);
+                float2 p2;
+                if (e % A2_POLY_EVERY == A2_POLY_EVERY - 1) {
+                    p2 = ex2_poly2(x2);
+                } else {
+                    p2.x = ex2_approx(x2.x);
+                    p2.y = ex2_approx(x2.y);
+                }
+                rs2 = fadd2(rs2, p2);
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(p2.x, p2.y);
+                pk[e] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            rs += rs2.x + rs2.y;
+        };
+        // O[32 x 64 slice of this warp] *= corr (per row), in tensor memory
+        auto rescale_o = [&](float corr) {
+#pragma unroll
+            for (int c = 0; c < AT_D; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(tO + lane_off + t * 64 + c, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * corr);
+                tmem_st32(tO + lane_off + t * 64 + c, v);
+            }
+        };
+        // one pass over S_j with reference `ref`: P_j -> TMEM; the next chunk's tcgen05.ld is in flight during the math
+        auto pass = [&](int j, float ref, float& rs, float& mxr, bool& o_waited) {
+            uint32_t va[32], vb[32];
+            tmem_ld32(tS + lane_off + t * 128, va);
+            tc_wait_ld();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t pk[16];
+                if (c + 1 < 4) {
+                    if (c & 1) tmem_ld32(tS + lane_off + t * 128 + (c + 1) * 32, va);
+                    else tmem_ld32(tS + lane_off + t * 128 + (c + 1) * 32, vb);
+                }
+                if (c & 1) exp_chunk(vb, ref, rs, mxr, pk);
+                else exp_chunk(va, ref, rs, mxr, pk);
+                if (c == 0 && j > 0 && !o_waited) {
+                    // PV_{j-1} has consumed P_{j-1}: the P columns may be overwritten
+                    mbar_wait(smem_u32(&o_full[t]), (j - 1) & 1);
+                    tc_fence_after();
+                    o_waited = true;
+                }
+                tmem_st16(tP + lane_off + t * 64 + c * 16, pk);
+                if (c + 1 < 4) tc_wait_ld();
+            }
+        };
+        for (int j = 0; j < ntiles; ++j) {
+            const uint32_t jp = j & 1;
+            mbar_wait(smem_u32(&s_full[t]), jp);
+            tc_fence_after();
+            bool o_waited = false;
+            if (pending) {
+                // the reference moves now: O (which includes PV_{j-1} once o_full fires) and l are rescaled first
+                mbar_wait(smem_u32(&o_full[t]), (j - 1) & 1);
+                tc_fence_after();
+                o_waited = true;
+                const float corr = ex2_approx(m_ref - pend_ref);
+                rescale_o(corr);
+                l *= corr;
+                m_ref = pend_ref;
+                pending = false;
+            }
+            float rs = 0.f, mxr = -INFINITY;
+            bool exact = (j == 0);
+            if (!exact) {
+                pass(j, m_ref, rs, mxr, o_waited);
+                exact = __any_sync(0xffffffffu, fmaf(mxr, sc, -m_ref) > 64.f);
+            }
+            if (exact) {
+                // exact two-pass scheme (first tile, or a score far above the reference): row maximum first
+                mxr = -INFINITY;
+#pragma unroll 1
+                for (int c = 0; c < AT_TK; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tS + lane_off + t * 128 + c, v);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) mxr = fmaxf(mxr, __uint_as_float(v[i]));
+                }
+                const float ref = fmaxf(m, mxr * sc);
+                if (j > 0) {
+                    if (!o_waited) {
+                        mbar_wait(smem_u32(&o_full[t]), (j - 1) & 1);
+                        tc_fence_after();
+                        o_waited = true;
+                    }
+                    const float corr = ex2_approx(m_ref - ref);
+                    rescale_o(corr);
+                    l *= corr;
+                }
+                m_ref = ref;
+                rs = 0.f;
+                float dummy = -INFINITY;
+                pass(j, m_ref, rs, dummy, o_waited);
+            }
+            l += rs;
+            m = fmaxf(m, mxr * sc);
+            // lazy reference: move it (before the next tile) only when the maximum has drifted 2^8 above it
+            if (__any_sync(0xffffffffu, m - m_ref > 8.f)) {
+                pending = true;
+                pend_ref = m;
+            }
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(smem_u32(&s_empty[t]));
+                mbar_arrive(smem_u32(&p_full[t]));
+            }
+        }
+        // final O: wait for the last PV MMA, normalise, store
+        mbar_wait(smem_u32(&o_full[t]), (ntiles - 1) & 1);
+        tc_fence_after();
+        const float inv = 1.f / l;
+        const long long row = (long long)row_base + q0 + t * AT_TQ + r;
+        __nv_bfloat16* op = p.out + row * p.C + h * AT_D;
+#pragma unroll
+        for (int c = 0; c < AT_D; c += 32) {
+            uint32_t v[32];
+            tmem_ld32(tO + lane_off + t * 64 + c, v);
+            tc_wait_ld();
+#pragma unroll
+            for (int d = 0; d < 32; d += 16) {
+                float o16[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) o16[e] = __uint_as_float(v[d + e]) * inv;
+                st16(op + c + d, o16);
+            }
+        }
+        p.lse[((long long)n * p.heads + h) * p.T + q0 + t * AT_TQ + r] = (m_ref + log2f(l)) * 0.6931471805599453f;
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 bool attention_tc_applicable(int N, int T, int heads, int dtype) {
     static int ok = -1;
     if (ok < 0) ok = pu_device_supports_tc();
@@ -592,6 +878,14 @@ int attention_fwd_tc(const void* qkv, void* out, float* lse, int N, int T, int h
     p.lse = lse;
     if (T % (2 * AT_TQ) == 0) {
         dim3 grid2(T / (2 * AT_TQ), N * heads);
+        // PU_ATTN_FWD: 3 (default) = O accumulated in tensor memory, 1.46 ms at T = 4096, heads 4, batch 64; 2 = the kernel
+        // that reads O back per key tile (1.71 ms; kept for A/B runs and the ablation switches)
+        static const int fwd_variant = getenv("PU_ATTN_FWD") ? atoi(getenv("PU_ATTN_FWD")) : 3;
+        if (fwd_variant == 3 && !getenv("PU_ATTN_FWD_ABL") && !getenv("PU_ATTN_FWD_POLY")) {
+            PU_SMEM_ATTR(attn_fwd_tc3_kernel, A2_SMEM);
+            attn_fwd_tc3_kernel<<<grid2, 384, A2_SMEM, st>>>(tm, p);
+            return check_launch("attn_fwd_tc3");
+        }
         static const int abl = getenv("PU_ATTN_FWD_ABL") ? atoi(getenv("PU_ATTN_FWD_ABL")) : 0;
         if (abl == 1) {
             PU_SMEM_ATTR(attn_fwd_tc2_kernel<1>, A2_SMEM);

@@ -28,6 +28,7 @@ print('RESULT fwd %.3f ms bwd %.3f ms' % (tf, tb))
 if __name__ == '__main__':
     runs = [('default', {})]
     runs += [(f'bwd {v}', {'PU_ATTN_BWD': str(v)}) for v in (20, 201, 204, 208, 212, 3, 301, 304, 305, 308, 312, 334)]
+    runs += [('fwd read-back', {'PU_ATTN_FWD': '2'})]
     runs += [(f'fwd abl {v}', {'PU_ATTN_FWD_ABL': str(v)}) for v in (1, 2, 5)]
     runs += [(f'fwd poly {v}', {'PU_ATTN_FWD_POLY': str(v)}) for v in (1, 2, 3)]
     

@@ -582,6 +582,23 @@ def test_attention_bwd_variants(variant):
     assert worst < 1.5e-2
 
 
+def test_attention_fwd_readback_variant():
+    """PU_ATTN_FWD=2 (attn_fwd_tc2_kernel: O read back from tensor memory after every key tile; the default is
+    attn_fwd_tc3_kernel with O accumulated in tensor memory and a lazily moved softmax reference): the forward parity tests
+    and the score-jump case again, in an interpreter of their own (the switch is read once per process)."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get('PU_ATTN_FWD'):
+        pytest.skip('already running under a PU_ATTN_FWD override')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(root, 'tests', 'test_ops_gpu.py'), '-q', '-m', 'gpu', '-x',
+                        '-k', 'test_attention_tc and not variant', '-p', 'no:cacheprovider'],
+                       capture_output=True, text=True, env=dict(os.environ, PU_ATTN_FWD='2'), timeout=900, cwd=root)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert '6 passed' in r.stdout, r.stdout[-1000:]
+
+
 def test_attention_tc_score_jumps():
     """The forward kernel's softmax uses the running maximum of the *previous* key tiles as the reference of the current
     one and falls back to the exact two-pass scheme when a score exceeds it by more than 2^64.  Build that case: keys in
