@@ -584,6 +584,7 @@ attn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdPara
 // fallback for scores more than 2^64 above the reference is kept.  With the registers that frees, the next 32-column
 // chunk of S is already in flight while the current one is exponentiated.
 // ------------------------------------------------------------------------------------------------
+template <int POLY_EVERY = A2_POLY_EVERY>
 __global__ void __launch_bounds__(384, 1)
 attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -718,7 +719,7 @@ attn_fwd_tc3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnFwdPara
                 mxr = fmaxf(fmaxf(s2.x, s2.y), mxr);
                 const float2 x2 = ffma2(s2, sc2, nref2);
                 float2 p2;
-                if (e % A2_POLY_EVERY == A2_POLY_EVERY - 1) {
+                if (POLY_EVERY > 0 && e % POLY_EVERY == POLY_EVERY - 1) {
                     p2 = ex2_poly2(x2);
                 } else {
                     p2.x = ex2_approx(x2.x);
@@ -882,8 +883,19 @@ int attention_fwd_tc(const void* qkv, void* out, float* lse, int N, int T, int h
         // that reads O back per key tile (1.71 ms; kept for A/B runs and the ablation switches)
         static const int fwd_variant = getenv("PU_ATTN_FWD") ? atoi(getenv("PU_ATTN_FWD")) : 3;
         if (fwd_variant == 3 && !getenv("PU_ATTN_FWD_ABL") && !getenv("PU_ATTN_FWD_POLY")) {
-            PU_SMEM_ATTR(attn_fwd_tc3_kernel, A2_SMEM);
-            attn_fwd_tc3_kernel<<<grid2, 384, A2_SMEM, st>>>(tm, p);
+            // every POLY-th pair of exponentials on the FMA pipe (ex2_poly2); measured at T = 4096: none 1.574 ms, every 2nd
+            // 1.467, 3rd 1.424, 4th 1.454, 6th 1.436, 8th 1.466
+            static const int poly3 = getenv("PU_ATTN_FWD3_POLY") ? atoi(getenv("PU_ATTN_FWD3_POLY")) : 3;
+            if (poly3 == 0) {
+                PU_SMEM_ATTR(attn_fwd_tc3_kernel<0>, A2_SMEM);
+                attn_fwd_tc3_kernel<0><<<grid2, 384, A2_SMEM, st>>>(tm, p);
+            } else if (poly3 == 4) {
+                PU_SMEM_ATTR(attn_fwd_tc3_kernel<4>, A2_SMEM);
+                attn_fwd_tc3_kernel<4><<<grid2, 384, A2_SMEM, st>>>(tm, p);
+            } else {
+                PU_SMEM_ATTR(attn_fwd_tc3_kernel<3>, A2_SMEM);
+                attn_fwd_tc3_kernel<3><<<grid2, 384, A2_SMEM, st>>>(tm, p);
+            }
             return check_launch("attn_fwd_tc3");
         }
         static const int abl = getenv("PU_ATTN_FWD_ABL") ? atoi(getenv("PU_ATTN_FWD_ABL")) : 0;
